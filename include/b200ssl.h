@@ -1,0 +1,233 @@
+/*
+ * b200ssl.h -- C ABI of the B200-native semi-supervised loss-and-mixing path.
+ *
+ * One shared library (libb200ssl.so, sm_100a) replaces the ATen call chains behind
+ * four Python modules of the reference (cowmix.py, lovasz.py, mean_teacher.py,
+ * metrics.py).  Every entry point cites the reference lines it stands in for.
+ *
+ * Conventions (all entry points)
+ *   - return 0 on success, a positive cudaError_t if a launch failed, a negative
+ *     B200SSL_E* code for argument errors; b200ssl_last_error() returns a
+ *     thread-local message for the last non-zero return.
+ *   - all data pointers are DEVICE pointers unless the name ends in `_host`.
+ *   - tensors are dense, row-major NCHW fp32 unless stated; labels are int64 by
+ *     default (torch.argmax convention), see b200ssl_label_dtype.
+ *   - the library allocates nothing, frees nothing, never synchronises and never
+ *     touches the legacy default stream: the caller owns every buffer and passes
+ *     a workspace (size from the matching *_workspace_bytes query) and a stream
+ *     (cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream).
+ *   - 16-byte aligned bases take the 128-bit path; other alignments fall back to
+ *     scalar accesses inside the same kernel (never an error).
+ */
+#ifndef B200SSL_H_
+#define B200SSL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define B200SSL_VERSION 100 /* 0.1.0 */
+
+#define B200SSL_EINVAL (-1)    /* bad argument */
+#define B200SSL_EWORKSPACE (-2) /* workspace too small */
+#define B200SSL_EUNSUPPORTED (-3)
+
+typedef void* b200ssl_stream_t; /* cudaStream_t */
+
+typedef enum b200ssl_label_dtype {
+  B200SSL_I64 = 0,
+  B200SSL_I32 = 1,
+  B200SSL_U8 = 2
+} b200ssl_label_dtype;
+
+int b200ssl_version(void);
+const char* b200ssl_last_error(void);
+/* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
+long long b200ssl_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Mean-teacher EMA over all parameter tensors in ONE launch.
+ * Replaces mean_teacher.update_ema_variables, reference mean_teacher.py:10-11
+ *     ema_param.data.mul_(alpha).add_(other=param.data, alpha=1. - alpha)
+ * Bit contract (fp32): t = RN(e * (float)alpha);  e' = fmaf(p, (float)(1.0 - alpha), t).
+ *
+ * The caller describes the tensors once; b200ssl_ema_build_table_host turns that into a chunk
+ * table (host memory), which the caller copies to the device and re-uses while the data
+ * pointers stay the same.
+ * --------------------------------------------------------------------------------------------- */
+#define B200SSL_EMA_CHUNK 4096 /* elements per table entry */
+
+typedef struct b200ssl_ema_chunk {
+  float* ema;        /* device pointer to first element of the chunk (teacher) */
+  const float* param; /* device pointer to first element of the chunk (student) */
+  int32_t count;     /* elements in this chunk, 1..B200SSL_EMA_CHUNK */
+  int32_t pad_;
+} b200ssl_ema_chunk;
+
+/* number of table entries needed for n_tensors tensors of the given element counts */
+int64_t b200ssl_ema_table_entries(const int64_t* numels_host, int n_tensors);
+/* fill table_host[0..entries); returns entries written or a negative error */
+int64_t b200ssl_ema_build_table_host(void* const* ema_ptrs_host, void* const* param_ptrs_host,
+                                     const int64_t* numels_host, int n_tensors,
+                                     b200ssl_ema_chunk* table_host, int64_t table_capacity);
+int b200ssl_ema_multi(const b200ssl_ema_chunk* table_dev, int64_t n_entries, double alpha,
+                      b200ssl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused CowMix mixing of up to two tensors that share one mask.
+ * Replaces two calls of cowmix.mix_with_mask, reference cowmix.py:72-73 (train.py:82,84-86)
+ *     tensor_a * mask + tensor_b * (1. - mask)
+ * evaluated as RN(RN(a*m) + RN(b*RN(1-m))) -- bit-identical to the four ATen kernels for any
+ * mask value (not only {0,1}), including inf/NaN propagation from the unselected operand.
+ *   a0,b0,out0 : [n, c0, hw]   (images)        a1,b1,out1 : [n, c1, hw] (predictions) or NULL,c1=0
+ *   mask       : [n, 1, hw]  if mask_channels==1, else [n, c, hw] (per-channel mask; requires c1==0)
+ * --------------------------------------------------------------------------------------------- */
+int b200ssl_mix2(const float* a0, const float* b0, float* out0, int c0, const float* a1,
+                 const float* b1, float* out1, int c1, const float* mask, int mask_channels,
+                 int64_t n, int64_t hw, b200ssl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CowMix mask generation from caller-supplied noise.
+ * Replaces cowmix.dual_pass_gaussian_fileter2d + the statistics/threshold tail of
+ * cowmix.generate_cowmix_masks_like, reference cowmix.py:27-37 and :56-68:
+ *     V[n,y,x] = sum_i taps[n,i] * noise[n, y+i-k, x]      (zero padded, k = K/2, i ascending)
+ *     S[n,y,x] = sum_j taps[n,j] * V[n, y, x+j-k]
+ *     tau_n    = thr_factor[n] * std_n(S, unbiased) + mean_n(S)
+ *     mask     = (S > tau_n) ? 1.f : 0.f
+ * taps are the reference's (off-centre) normalised Gaussian weights, computed by the caller on
+ * the host exactly as cowmix.py:6-24 does and uploaded ([n, K] fp32, K odd).
+ * thr_factor[n] = erfinv(2p-1)*sqrt(2) (cowmix.py:64), also caller-computed.
+ * field_out (optional, may be NULL) receives S for diagnostics/parity margins.
+ * --------------------------------------------------------------------------------------------- */
+size_t b200ssl_cowmix_workspace_bytes(int n, int h, int w);
+int b200ssl_cowmix_mask(const float* noise, const float* taps, int K, const float* thr_factor,
+                        int n, int h, int w, float* mask_out, float* field_out, void* workspace,
+                        size_t workspace_bytes, b200ssl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Lovasz-softmax forward (+ unit gradients) and backward.
+ * Replaces lovasz.lovasz_softmax / lovasz_softmax_flat / flatten_probas / lovasz_grad,
+ * reference lovasz.py:155-170, :173-201, :204-220, :19-31, and autograd's backward of them.
+ *
+ * A *segment* is one (image-group, class) pair that the reference sorts on its own:
+ *   per_image != 0 : n_groups = n_images, segment length L = hw
+ *   per_image == 0 : n_groups = 1,        segment length L = n_images*hw
+ * Classes summed: class_mode ALL/PRESENT -> 0..C-1, LIST -> class_list[0..n_list).
+ * Segment order: seg = group * n_cls + class_slot.
+ *
+ * Forward writes, per segment s:
+ *   seg_loss[s]    fp32  dot(errors_sorted, lovasz_grad(fg_sorted))             (lovasz.py:200)
+ *   seg_fg[s]      int32 number of valid foreground pixels (0 => absent class)   (lovasz.py:188)
+ *   seg_valid[s]   int32 number of non-ignored pixels
+ * and, for every pixel i of every summed class c, the unit gradient
+ *   jgrad[n,c,i] = sign(p - fg) * (J[rank] - J[rank-1])      (0 for ignored pixels)
+ * computed with the reference's fp32 operation sequence (integer counts -> IEEE div ->
+ * 1-q -> adjacent difference), ties ordered by ascending pixel index (stable).
+ * Planes of classes that are not summed are zero-filled.
+ * loss_out (optional) receives lovasz_softmax's scalar: mean over groups of the mean over
+ * counted classes (PRESENT skips seg_fg==0), sequential fp32 sums as lovasz.py:235-253.
+ *
+ * Backward: grad_probas[n,c,i] = seg_scale[seg(n,c)] * jgrad[n,c,i] (in place allowed).
+ * b200ssl_lovasz_seg_scale derives seg_scale from the scalar upstream gradient for loss_out.
+ * --------------------------------------------------------------------------------------------- */
+#define B200SSL_LOVASZ_ALL 0
+#define B200SSL_LOVASZ_PRESENT 1
+#define B200SSL_LOVASZ_LIST 2
+#define B200SSL_LOVASZ_MAX_LIST 64
+
+typedef struct b200ssl_lovasz_desc {
+  int32_t n_images;
+  int32_t n_channels;   /* C of probas; 1 = sigmoid mode (class_pred = probas[:,0]) */
+  int64_t hw;           /* H*W */
+  int32_t per_image;
+  int32_t class_mode;   /* B200SSL_LOVASZ_* */
+  int32_t n_list;
+  int32_t class_list[B200SSL_LOVASZ_MAX_LIST];
+  int32_t has_ignore;
+  int64_t ignore_index;
+  int32_t label_dtype;  /* b200ssl_label_dtype */
+  int32_t reserved_;
+} b200ssl_lovasz_desc;
+
+int32_t b200ssl_lovasz_num_segments(const b200ssl_lovasz_desc* d);
+size_t b200ssl_lovasz_workspace_bytes(const b200ssl_lovasz_desc* d);
+int b200ssl_lovasz_forward(const b200ssl_lovasz_desc* d, const float* probas, const void* labels,
+                           float* loss_out, float* seg_loss, int32_t* seg_fg, int32_t* seg_valid,
+                           float* jgrad, void* workspace, size_t workspace_bytes,
+                           b200ssl_stream_t stream);
+int b200ssl_lovasz_seg_scale(const b200ssl_lovasz_desc* d, const float* grad_out,
+                             const int32_t* seg_fg, const int32_t* seg_valid, float* seg_scale,
+                             b200ssl_stream_t stream);
+int b200ssl_lovasz_backward(const b200ssl_lovasz_desc* d, const float* seg_scale,
+                            const float* jgrad, float* grad_probas, b200ssl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * losses.binary_lovasz_loss_with_logits glue, reference losses.py:239-250:
+ *     int_target = argmax(target, 1);  per sample i:  w_i = (int_target_i.sum() > 0)
+ *     loss = sum_i w_i * L_i / (sum_i w_i + 0.001)         (python left-to-right fp32 sums)
+ * b200ssl_argmax_channels turns the soft one-hot target [n, C, hw] into integer labels
+ * (first maximum wins, as torch.argmax; NaN counts as maximum) and counts the non-zero labels
+ * per image (nonzero_out: int32 [n], ACCUMULATED; may be NULL).  out_dtype: B200SSL_I64 or
+ * B200SSL_U8 (C <= 256).
+ * b200ssl_binary_lovasz_reduce evaluates the weighted mean from the per-image Lovasz losses
+ * L_i (seg_loss of a per_image, single-class forward); *_scale produces the per-segment upstream
+ * gradients RN(grad_out / denom) * w_i for b200ssl_lovasz_backward.
+ * --------------------------------------------------------------------------------------------- */
+int b200ssl_argmax_channels(const float* x, int n_images, int n_channels, int64_t hw,
+                            void* labels_out, int out_dtype, int32_t* nonzero_out,
+                            b200ssl_stream_t stream);
+int b200ssl_binary_lovasz_reduce(const float* seg_loss, const int32_t* nonzero, int n,
+                                 float* loss_out, float* denom_out, b200ssl_stream_t stream);
+int b200ssl_binary_lovasz_scale(const float* grad_out, const int32_t* nonzero,
+                                const float* denom, int n, float* seg_scale,
+                                b200ssl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Confusion matrix (new component; the reference only has its derived quantities:
+ * metrics.dice_metric metrics.py:1-7 and lovasz.iou lovasz.py:54-73).
+ *     cm[l*D + p] += 1   for every pixel with label != ignore_index
+ * cm is int64 [D*D] and is ACCUMULATED into (zero it first for a fresh matrix).
+ *   other_bucket == 0: D = C; pixels whose label (other than ignore_index) or prediction is
+ *       outside [0,C) are not counted; their number is added to *dropped (optional int64 scalar).
+ *   other_bucket != 0: D = C+1; out-of-range labels / predictions are counted in row / column C
+ *       (needed to reproduce lovasz.iou's union exactly when predictions contain void classes).
+ * If per_image != 0, cm is [n_pixels/hw, D*D] and pixel i goes to image i / hw.
+ * --------------------------------------------------------------------------------------------- */
+int b200ssl_confusion_matrix(const void* labels, const void* preds, int64_t n_pixels,
+                             int num_classes, int other_bucket, int has_ignore,
+                             int64_t ignore_index, int label_dtype, int per_image, int64_t hw,
+                             long long* cm, long long* dropped, b200ssl_stream_t stream);
+
+/* Fused argmax + confusion matrix straight from logits ("next" row N3 of SURVEY 8f):
+ *   pred = argmax_c logits[n,c,i] (first maximum wins, as torch.argmax), then as above (D = C). */
+int b200ssl_confusion_from_logits(const float* logits, const void* labels, int n_images,
+                                  int num_classes, int64_t hw, int has_ignore, int64_t ignore_index,
+                                  int label_dtype, int per_image, long long* cm, long long* dropped,
+                                  b200ssl_stream_t stream);
+
+/* metrics.dice_metric, reference metrics.py:1-7, for input/target [n, chw] fp32:
+ *   dice[i] = (2*sum(x*y) + 1) / (sum(x+y) + 1); sums accumulated in fp64 then rounded to fp32
+ *   (exact, hence identical to the reference, for {0,1} inputs below 2^24 elements). */
+int b200ssl_dice_metric(const float* input, const float* target, int n, int64_t chw,
+                        float* dice_out, void* workspace, size_t workspace_bytes,
+                        b200ssl_stream_t stream);
+size_t b200ssl_dice_workspace_bytes(int n, int64_t chw);
+
+/* the same quantity from per-image 2x2 confusion matrices [n][4] = {TN, FP, FN, TP}:
+ *   dice[n] = (2*TP + 1) / (2*TP + FP + FN + 1)  evaluated in fp32 like the reference. */
+int b200ssl_dice_from_cm(const long long* cm_per_image, int n_images, float* dice_out,
+                         b200ssl_stream_t stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SSL_H_ */

@@ -1,0 +1,147 @@
+"""ctypes binding of libb200ssl.so (the C ABI declared in include/b200ssl.h).
+
+The product path has no CPU fallback: if the CUDA library has not been built this module
+raises at import time, and every op raises if it is handed a non-CUDA tensor.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200ssl.so")
+
+MAX_LIST = 64
+I64, I32, U8 = 0, 1, 2
+LOVASZ_ALL, LOVASZ_PRESENT, LOVASZ_LIST = 0, 1, 2
+EMA_CHUNK = 4096
+
+
+class LovaszDesc(C.Structure):
+    _fields_ = [
+        ("n_images", C.c_int32),
+        ("n_channels", C.c_int32),
+        ("hw", C.c_int64),
+        ("per_image", C.c_int32),
+        ("class_mode", C.c_int32),
+        ("n_list", C.c_int32),
+        ("class_list", C.c_int32 * MAX_LIST),
+        ("has_ignore", C.c_int32),
+        ("ignore_index", C.c_int64),
+        ("label_dtype", C.c_int32),
+        ("reserved_", C.c_int32),
+    ]
+
+
+class EmaChunk(C.Structure):
+    _fields_ = [("ema", C.c_void_p), ("param", C.c_void_p), ("count", C.c_int32), ("pad_", C.c_int32)]
+
+
+_vp, _i, _i64, _sz, _d = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
+
+# name -> (restype, argtypes); mirrors include/b200ssl.h one to one
+SIGNATURES = {
+    "b200ssl_version": (_i, []),
+    "b200ssl_last_error": (C.c_char_p, []),
+    "b200ssl_launch_count": (C.c_longlong, []),
+    "b200ssl_ema_table_entries": (_i64, [_vp, _i]),
+    "b200ssl_ema_build_table_host": (_i64, [_vp, _vp, _vp, _i, _vp, _i64]),
+    "b200ssl_ema_multi": (_i, [_vp, _i64, _d, _vp]),
+    "b200ssl_mix2": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i64, _i64, _vp]),
+    "b200ssl_cowmix_workspace_bytes": (_sz, [_i, _i, _i]),
+    "b200ssl_cowmix_mask": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "b200ssl_lovasz_num_segments": (C.c_int32, [C.POINTER(LovaszDesc)]),
+    "b200ssl_lovasz_workspace_bytes": (_sz, [C.POINTER(LovaszDesc)]),
+    "b200ssl_lovasz_forward": (_i, [C.POINTER(LovaszDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200ssl_lovasz_seg_scale": (_i, [C.POINTER(LovaszDesc), _vp, _vp, _vp, _vp, _vp]),
+    "b200ssl_lovasz_backward": (_i, [C.POINTER(LovaszDesc), _vp, _vp, _vp, _vp]),
+    "b200ssl_argmax_channels": (_i, [_vp, _i, _i, _i64, _vp, _i, _vp, _vp]),
+    "b200ssl_binary_lovasz_reduce": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "b200ssl_binary_lovasz_scale": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "b200ssl_confusion_matrix": (_i, [_vp, _vp, _i64, _i, _i, _i, _i64, _i, _i, _i64, _vp, _vp, _vp]),
+    "b200ssl_confusion_from_logits": (_i, [_vp, _vp, _i, _i, _i64, _i, _i64, _i, _i, _vp, _vp, _vp]),
+    "b200ssl_dice_workspace_bytes": (_sz, [_i, _i64]),
+    "b200ssl_dice_metric": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _sz, _vp]),
+    "b200ssl_dice_from_cm": (_i, [_vp, _i, _vp, _vp]),
+}
+
+
+class B200SSLError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C semi-supervised_semantic_segmentation_b200/csrc` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means header and library are out of sync
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib.b200ssl_last_error().decode("utf-8", "replace")
+        raise B200SSLError(f"{what or 'b200ssl'} failed (rc={rc}): {msg}")
+
+
+def launch_count():
+    return int(lib.b200ssl_launch_count())
+
+
+def stream_ptr(device=None):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t, name, dtype=None):
+    """The product path runs on the GPU or not at all."""
+    import torch
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"b200ssl: {name} is on {t.device}; the B200 kernels have no CPU fallback "
+            "(use the reference implementation for CPU tensors)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"b200ssl: {name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def label_dtype_code(t):
+    import torch
+    if t.dtype == torch.int64:
+        return I64
+    if t.dtype == torch.int32:
+        return I32
+    if t.dtype == torch.uint8:
+        return U8
+    raise TypeError(f"b200ssl: labels must be int64, int32 or uint8, got {t.dtype}")
+
+
+class WorkspaceCache:
+    """One growing scratch tensor per (device, tag); allocation is PyTorch's (caching allocator),
+    the library itself never allocates."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, device, tag, nbytes):
+        import torch
+        key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._bufs[key] = buf
+        return buf
+
+    def clear(self):
+        self._bufs.clear()
+
+
+workspaces = WorkspaceCache()

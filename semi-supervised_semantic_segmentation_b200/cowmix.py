@@ -1,0 +1,166 @@
+"""Drop-in for the reference's cowmix.py (same function names and argument meaning).
+
+    reference cowmix.py:40-69  generate_cowmix_masks_like  -> b200ssl_cowmix_mask
+    reference cowmix.py:72-73  mix_with_mask               -> b200ssl_mix2
+
+Host-side work is limited to what the reference also does on the host: the 2N uniform draws
+for p and sigma (CPU generator), the N*K normalised Gaussian taps and the N erfinv threshold
+factors; they are uploaded in one pinned, non-blocking copy.  Everything that touches pixels runs
+in the CUDA library.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, stream_ptr, require_cuda
+
+
+def kernel_size_for(sigma_max):
+    """cowmix.py:30 -- `int(round(sigma_max * 3) * 2) + 1` with Python's half-to-even round."""
+    return int(round(sigma_max * 3) * 2) + 1
+
+
+def gaussian_taps(size, sigmas):
+    """All per-sample tap vectors at once: [N, size] fp32 on the CPU.
+
+    Batched restatement of cowmix.py:6-24.  For odd `size` the abscissa runs from -(k+1) to k-1
+    (the reference's arange(-size//2, size//2)), i.e. the peak sits one tap right of centre.
+    Every elementwise op is the same ATen CPU op the reference issues per sample, so the values
+    are bit-identical to the reference's (tests/test_cowmix_host.py checks this).
+    """
+    x = torch.arange(-size // 2, size // 2).float()
+    if size % 2 == 0:
+        x = x + 0.5
+    denom = 2 * sigmas.float() ** 2                      # float(2 * sigma ** 2) per sample
+    g = torch.exp(-x.pow(2.0).unsqueeze(0) / denom.unsqueeze(1))
+    norm = torch.stack([row.sum() for row in g])        # 1-D sums, the reference's reduction order
+    return (g / norm.unsqueeze(1)).contiguous()
+
+
+def draw_mask_parameters(n, mask_proportion_range, sigma_range):
+    """cowmix.py:44-51: p ~ U(lo,hi), sigma ~ logU(lo,hi), both from the CPU generator, p first."""
+    p_distribution = torch.distributions.Uniform(torch.tensor(mask_proportion_range[0]),
+                                                 torch.tensor(mask_proportion_range[1]))
+    p = p_distribution.rsample(sample_shape=[n])
+    log_lo, log_hi = math.log(float(sigma_range[0])), math.log(float(sigma_range[1]))
+    sigma_distribution = torch.distributions.Uniform(torch.tensor(log_lo), torch.tensor(log_hi))
+    sigmas = torch.exp(sigma_distribution.rsample([n]))
+    return p, sigmas
+
+
+def masks_from_noise(noise, p, sigmas, return_field=False):
+    """Deterministic tail of generate_cowmix_masks_like (cowmix.py:56-68) for a given noise field.
+
+    noise: [N,1,H,W] fp32 CUDA; p, sigmas: [N] CPU tensors.  Returns mask [N,1,H,W] (and the
+    smoothed field S when return_field is set).
+    """
+    require_cuda(noise, "noise", torch.float32)
+    if noise.dim() != 4 or noise.shape[1] != 1:
+        raise ValueError("noise must be [N,1,H,W]")
+    n, _, h, w = noise.shape
+    assert n == sigmas.shape[0]  # cowmix.py:29
+    noise = noise.contiguous()
+    mask = torch.empty_like(noise)
+    field = torch.empty_like(noise) if return_field else None
+    if n == 0 or h == 0 or w == 0:
+        return (mask, field) if return_field else mask
+    size = kernel_size_for(sigmas.max().item())
+    taps = gaussian_taps(size, sigmas)
+    factors = (torch.erfinv(2 * p - 1) * math.sqrt(2.0)).float()          # cowmix.py:64
+    host = torch.empty(n * size + n, dtype=torch.float32, pin_memory=True)
+    host[: n * size] = taps.reshape(-1)
+    host[n * size:] = factors.reshape(-1)
+    dev = host.to(noise.device, non_blocking=True)
+    ws_bytes = lib.b200ssl_cowmix_workspace_bytes(n, h, w)
+    ws = _lib.workspaces.get(noise.device, "cowmix", ws_bytes)
+    with torch.cuda.device(noise.device):
+        check(lib.b200ssl_cowmix_mask(
+            noise.data_ptr(), dev.data_ptr(), size, dev.data_ptr() + 4 * n * size, n, h, w,
+            mask.data_ptr(), field.data_ptr() if return_field else None, ws.data_ptr(), ws.numel(),
+            stream_ptr(noise.device)), "cowmix_mask")
+    return (mask, field) if return_field else mask
+
+
+def generate_cowmix_masks_like(example_tensor, mask_proportion_range, sigma_range):
+    # mask_proportion range: tuple of 2 python floats; sigma_range: tuple of 2 python floats
+    require_cuda(example_tensor, "example_tensor")
+    if example_tensor.dtype != torch.float32:
+        raise TypeError("b200ssl.cowmix: only float32 is supported (the reference trains in fp32)")
+    with torch.no_grad():
+        n = example_tensor.size(0)
+        p, sigmas = draw_mask_parameters(n, mask_proportion_range, sigma_range)
+        size = list(example_tensor.size())
+        size[1] = 1
+        # device generator, drawn after the CPU draws exactly like cowmix.py:53-55
+        noise = torch.normal(mean=0, std=1, size=size, dtype=example_tensor.dtype,
+                             device=example_tensor.device)
+        return masks_from_noise(noise, p, sigmas)
+
+
+def _as_nchw(t):
+    if t.dim() < 2:
+        raise ValueError("mix_with_mask expects tensors with a batch and a channel dimension")
+    return t.contiguous()
+
+
+def mix2_with_mask(a0, b0, a1, b1, mask):
+    """Fused `mix_with_mask(a0,b0,mask), mix_with_mask(a1,b1,mask)` (train.py:82-86) in one launch.
+    a*: [N,C*,H,W]; mask: [N,1,H,W].  Pass a1=b1=None to mix a single pair."""
+    require_cuda(mask, "mask", torch.float32)
+    a0 = _as_nchw(require_cuda(a0, "tensor_a", torch.float32))
+    b0 = _as_nchw(require_cuda(b0, "tensor_b", torch.float32))
+    if a0.shape != b0.shape:
+        raise ValueError("tensor_a and tensor_b must have the same shape")
+    n, c0 = a0.shape[0], a0.shape[1]
+    hw = a0[0, 0].numel() if a0.numel() else 0
+    mask = mask.contiguous()
+    per_channel = mask.shape == a0.shape and c0 != 1
+    if not per_channel and (mask.shape[0] != n or mask.shape[1] != 1 or mask[0, 0].numel() != hw):
+        raise ValueError(f"mask shape {tuple(mask.shape)} does not broadcast over {tuple(a0.shape)} as [N,1,H,W]")
+    out0 = torch.empty_like(a0)
+    out1 = None
+    c1 = 0
+    if a1 is not None:
+        if per_channel:
+            raise ValueError("a per-channel mask cannot be shared with a second tensor pair")
+        a1 = _as_nchw(require_cuda(a1, "tensor_a1", torch.float32))
+        b1 = _as_nchw(require_cuda(b1, "tensor_b1", torch.float32))
+        if a1.shape != b1.shape or a1.shape[0] != n or (a1[0, 0].numel() if a1.numel() else 0) != hw:
+            raise ValueError("second tensor pair must share batch and spatial size with the first")
+        c1 = a1.shape[1]
+        out1 = torch.empty_like(a1)
+    with torch.cuda.device(a0.device):
+        check(lib.b200ssl_mix2(
+            a0.data_ptr(), b0.data_ptr(), out0.data_ptr(), c0,
+            a1.data_ptr() if c1 else None, b1.data_ptr() if c1 else None,
+            out1.data_ptr() if c1 else None, c1, mask.data_ptr(), c0 if per_channel else 1,
+            n, hw, stream_ptr(a0.device)), "mix2")
+    return out0, out1
+
+
+class _Mix(torch.autograd.Function):
+    """Autograd-transparent like the reference's arithmetic: d/da = mask, d/db = 1 - mask."""
+
+    @staticmethod
+    def forward(ctx, tensor_a, tensor_b, mask):
+        ctx.save_for_backward(mask)
+        return mix2_with_mask(tensor_a, tensor_b, None, None, mask)[0]
+
+    @staticmethod
+    def backward(ctx, grad):
+        (mask,) = ctx.saved_tensors
+        zero = torch.zeros_like(grad)
+        ga = mix2_with_mask(grad, zero, None, None, mask)[0] if ctx.needs_input_grad[0] else None
+        gb = mix2_with_mask(zero, grad, None, None, mask)[0] if ctx.needs_input_grad[1] else None
+        return ga, gb, None
+
+
+def mix_with_mask(tensor_a, tensor_b, mask):
+    """cowmix.py:72-73: tensor_a * mask + tensor_b * (1. - mask), bit-identical evaluation order."""
+    if torch.is_grad_enabled() and (tensor_a.requires_grad or tensor_b.requires_grad):
+        if mask.requires_grad:
+            raise NotImplementedError("b200ssl.cowmix.mix_with_mask: gradient w.r.t. the mask is not supported")
+        return _Mix.apply(tensor_a, tensor_b, mask)
+    return mix2_with_mask(tensor_a, tensor_b, None, None, mask)[0]

@@ -1,0 +1,368 @@
+// Confusion matrix cm[label*C + pred] as a shared-memory-privatised histogram, plus the fused
+// argmax-from-logits variant and Dice from per-image 2x2 matrices.
+//
+// No reference function computes a confusion matrix; the quantities derived from it
+// are metrics.dice_metric (metrics.py:1-7) and lovasz.iou (lovasz.py:54-73).  The restated oracle
+// is bincount(label*C + pred, minlength=C*C) over the non-ignored pixels.
+//
+// Segmentation labels are spatially coherent, so most of a warp hits the same bin.  A per-pixel
+// shared-memory atomic would serialise (32 cycles per warp on one bank); instead each warp finds
+// the runs of equal bins among adjacent lanes with one shuffle + one ballot and issues ONE atomic
+// per run.  Each warp owns a private histogram copy when C*C is small enough, so there is no
+// inter-warp contention either.  Counts are exact integers: results are bit-identical to the oracle.
+//
+// Roofline: HBM-bound, 16 B/pixel with int64 label+pred (2 B/pixel with uint8).
+#include "common.cuh"
+
+namespace b200ssl {
+
+constexpr int kCmThreads = 256;
+constexpr int kCmWarps = kCmThreads / 32;
+constexpr int kCmSmemBudget = 64 * 1024;
+
+template <typename T>
+__device__ __forceinline__ int make_bin(T l, T p, int C, int D, bool has_ignore, long long ignore,
+                                        unsigned& dropped) {
+  long long ll = (long long)l, pp = (long long)p;
+  if (has_ignore && ll == ignore) return -1;
+  const bool lo = (ll < 0 || ll >= C), po = (pp < 0 || pp >= C);
+  if (lo || po) {
+    if (D == C) {  // no "other" bucket: drop and count
+      ++dropped;
+      return -1;
+    }
+    if (lo) ll = C;
+    if (po) pp = C;
+  }
+  return (int)ll * D + (int)pp;
+}
+
+// flush a block's private copies into the global int64 matrix
+__device__ __forceinline__ void flush_hist(const unsigned* hist, int copies, int bins,
+                                           unsigned long long* cm) {
+  for (int b = threadIdx.x; b < bins; b += blockDim.x) {
+    unsigned long long s = 0;
+    for (int c = 0; c < copies; ++c) s += hist[c * bins + b];
+    if (s) atomicAdd(cm + b, s);
+  }
+}
+
+// T = label/pred element type, ELEMS = elements per 16-byte vector (1 => scalar loads)
+template <typename T, int ELEMS>
+__global__ void __launch_bounds__(kCmThreads)
+confusion_kernel(const T* __restrict__ labels, const T* __restrict__ preds, long long plane_pixels,
+                 int C, int D, bool has_ignore, long long ignore, int copies,
+                 unsigned long long* __restrict__ cm, long long cm_plane_stride,
+                 unsigned long long* __restrict__ dropped_out) {
+  extern __shared__ unsigned smem_hist[];
+  const int bins = D * D;
+  const bool use_smem = copies > 0;
+  labels += (long long)blockIdx.y * plane_pixels;
+  preds += (long long)blockIdx.y * plane_pixels;
+  cm += (long long)blockIdx.y * cm_plane_stride;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < copies * bins; i += blockDim.x) smem_hist[i] = 0;
+    __syncthreads();
+  }
+  const int warp = threadIdx.x >> 5;
+  // a warp's histogram: its private copy, a shared copy, or the global matrix itself (32-bit view
+  // is not possible there, so the global fallback uses 64-bit atomics below)
+  unsigned* my_hist = use_smem ? smem_hist + (warp % copies) * bins : nullptr;
+
+  union Vec { uint4 u; T e[ELEMS > 1 ? ELEMS : 1]; };
+  constexpr int kPerGroup = 32 * ELEMS;
+  const long long n_groups = (plane_pixels + kPerGroup - 1) / kPerGroup;
+  // contiguous range of warp-groups per block
+  const long long per_block = (n_groups + gridDim.x - 1) / gridDim.x;
+  const long long g_begin = (long long)blockIdx.x * per_block;
+  const long long g_end = min(n_groups, g_begin + per_block);
+  unsigned dropped = 0;
+  constexpr int kUnroll = 4;
+  for (long long g0 = g_begin + warp; g0 < g_end; g0 += (long long)kCmWarps * kUnroll) {
+    Vec lv[kUnroll], pv[kUnroll];
+    bool full[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long g = g0 + (long long)u * kCmWarps;
+      const long long first = (g * 32 + lane_id()) * ELEMS;
+      full[u] = (g < g_end) && (first + ELEMS <= plane_pixels);
+      if (full[u]) {
+        if (ELEMS > 1) {
+          lv[u].u = __ldg(reinterpret_cast<const uint4*>(labels + first));
+          pv[u].u = __ldg(reinterpret_cast<const uint4*>(preds + first));
+        } else {
+          lv[u].e[0] = __ldg(labels + first);
+          pv[u].e[0] = __ldg(preds + first);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long g = g0 + (long long)u * kCmWarps;
+      if (g >= g_end) break;  // warp-uniform
+      const long long first = (g * 32 + lane_id()) * ELEMS;
+#pragma unroll
+      for (int e = 0; e < ELEMS; ++e) {
+        int bin = -1;
+        if (full[u]) {
+          bin = make_bin<T>(lv[u].e[e], pv[u].e[e], C, D, has_ignore, ignore, dropped);
+        } else if (first + e < plane_pixels) {  // ragged tail of the plane: scalar loads
+          bin = make_bin<T>(labels[first + e], preds[first + e], C, D, has_ignore, ignore, dropped);
+        }
+        if (use_smem) {
+          warp_run_add(my_hist, bin);
+        } else {
+          // very large C: the matrix does not fit in shared memory, merge runs then go to L2
+          const unsigned lane = lane_id();
+          const int prev = __shfl_up_sync(0xffffffffu, bin, 1);
+          const bool head = (lane == 0) || (bin != prev);
+          const unsigned heads = __ballot_sync(0xffffffffu, head);
+          if (head && bin >= 0) {
+            const unsigned later = (lane == 31) ? 0u : (heads & (0xffffffffu << (lane + 1)));
+            const int end = later ? (__ffs(later) - 1) : 32;
+            atomicAdd(cm + bin, (unsigned long long)(end - (int)lane));
+          }
+        }
+      }
+    }
+  }
+  if (dropped_out) {
+    const unsigned d = warp_sum(dropped);
+    if (lane_id() == 0 && d) atomicAdd(dropped_out, (unsigned long long)d);
+  }
+  if (use_smem) {
+    __syncthreads();
+    flush_hist(smem_hist, copies, bins, cm);
+  }
+}
+
+// ---- fused argmax + confusion matrix from logits -----------------------------------------------
+// logits [n_images, C, hw] fp32; each lane owns 4 consecutive pixels (float4 per channel).
+template <typename T>
+__global__ void __launch_bounds__(kCmThreads)
+confusion_logits_kernel(const float* __restrict__ logits, const T* __restrict__ labels,
+                        long long hw, int C, int D, bool has_ignore, long long ignore, int copies,
+                        bool vec_ok, unsigned long long* __restrict__ cm,
+                        long long cm_plane_stride, unsigned long long* __restrict__ dropped_out) {
+  extern __shared__ unsigned smem_hist[];
+  const int bins = D * D;
+  const bool use_smem = copies > 0;
+  logits += (long long)blockIdx.y * C * hw;
+  labels += (long long)blockIdx.y * hw;
+  cm += (long long)blockIdx.y * cm_plane_stride;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < copies * bins; i += blockDim.x) smem_hist[i] = 0;
+    __syncthreads();
+  }
+  const int warp = threadIdx.x >> 5;
+  unsigned* my_hist = use_smem ? smem_hist + (warp % copies) * bins : nullptr;
+  constexpr int kPerGroup = 32 * 4;
+  const long long n_groups = (hw + kPerGroup - 1) / kPerGroup;
+  const long long per_block = (n_groups + gridDim.x - 1) / gridDim.x;
+  const long long g_begin = (long long)blockIdx.x * per_block;
+  const long long g_end = min(n_groups, g_begin + per_block);
+  unsigned dropped = 0;
+  for (long long g = g_begin + warp; g < g_end; g += kCmWarps) {
+    const long long first = (g * 32 + lane_id()) * 4;
+    float best[4];
+    int arg[4];
+    const bool full = vec_ok && (first + 4 <= hw);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { best[e] = 0.f; arg[e] = -1; }
+    if (full) {
+      // torch.argmax: first maximal element wins; NaN counts as the maximum
+      for (int c0 = 0; c0 < C; c0 += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (c0 + u < C) v[u] = ld_stream_f4(logits + (long long)(c0 + u) * hw + first);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (c0 + u < C) {
+            const float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const bool take = (arg[e] < 0) || (x[e] > best[e]) || (x[e] != x[e] && best[e] == best[e]);
+              if (take) { best[e] = x[e]; arg[e] = c0 + u; }
+            }
+          }
+        }
+      }
+    } else {
+      for (int e = 0; e < 4; ++e) {
+        if (first + e < hw) {
+          for (int c = 0; c < C; ++c) {
+            const float x = logits[(long long)c * hw + first + e];
+            const bool take = (arg[e] < 0) || (x > best[e]) || (x != x && best[e] == best[e]);
+            if (take) { best[e] = x; arg[e] = c; }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int bin = -1;
+      if (first + e < hw) {
+        bin = make_bin<long long>((long long)labels[first + e], (long long)arg[e], C, D, has_ignore,
+                                  ignore, dropped);
+      }
+      if (use_smem) {
+        warp_run_add(my_hist, bin);
+      } else if (bin >= 0) {
+        atomicAdd(cm + bin, 1ull);
+      }
+    }
+  }
+  if (dropped_out) {
+    const unsigned d = warp_sum(dropped);
+    if (lane_id() == 0 && d) atomicAdd(dropped_out, (unsigned long long)d);
+  }
+  if (use_smem) {
+    __syncthreads();
+    flush_hist(smem_hist, copies, bins, cm);
+  }
+}
+
+// metrics.py:1-7 on {0,1} inputs: intersection = TP, cardinality = 2TP + FP + FN (fp32 sums of
+// integers); dice = (2*I + 1) / (card + 1), each op rounded to fp32 like the ATen chain.
+__global__ void dice_from_cm_kernel(const long long* __restrict__ cm, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long fp = cm[4 * i + 1], fn = cm[4 * i + 2], tp = cm[4 * i + 3];
+  const float inter = __ll2float_rn(tp);
+  const float card = __ll2float_rn(2 * tp + fp + fn);
+  out[i] = __fdiv_rn(__fadd_rn(__fmul_rn(2.0f, inter), 1.0f), __fadd_rn(card, 1.0f));
+}
+
+static int cm_copies(int D) {
+  const long long bytes = (long long)D * D * 4;
+  long long copies = kCmSmemBudget / bytes;
+  if (copies > kCmWarps) copies = kCmWarps;
+  return (int)copies;  // 0 => global atomics
+}
+
+template <typename T, int ELEMS>
+static int launch_confusion(const void* labels, const void* preds, long long plane_pixels,
+                            int planes, int C, int D, bool has_ignore, long long ignore,
+                            unsigned long long* cm, long long cm_stride,
+                            unsigned long long* dropped, cudaStream_t s) {
+  const int copies = cm_copies(D);
+  const size_t smem = (size_t)copies * D * D * 4;
+  const long long groups = (plane_pixels + 32 * ELEMS - 1) / (32 * ELEMS);
+  // enough work per block to amortise the histogram flush; never more than 8 CTAs per SM in total
+  long long bx = (groups + kCmWarps * 4 - 1) / (kCmWarps * 4);
+  long long cap = (long long)kNumSMs * 8 / planes;
+  if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  auto kern = confusion_kernel<T, ELEMS>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<dim3((unsigned)bx, (unsigned)planes), kCmThreads, smem, s>>>(
+      static_cast<const T*>(labels), static_cast<const T*>(preds), plane_pixels, C, D, has_ignore,
+      ignore, copies, cm, cm_stride, dropped);
+  return check_launch("confusion_matrix");
+}
+
+}  // namespace b200ssl
+
+extern "C" {
+
+int b200ssl_confusion_matrix(const void* labels, const void* preds, int64_t n_pixels,
+                             int num_classes, int other_bucket, int has_ignore,
+                             int64_t ignore_index, int label_dtype, int per_image, int64_t hw,
+                             long long* cm, long long* dropped, b200ssl_stream_t stream) {
+  using namespace b200ssl;
+  B200SSL_REQUIRE(n_pixels >= 0, "confusion_matrix: negative pixel count");
+  B200SSL_REQUIRE(num_classes >= 1 && num_classes <= 4096, "confusion_matrix: num_classes out of range");
+  B200SSL_REQUIRE(cm != nullptr, "confusion_matrix: null cm");
+  if (n_pixels == 0) return 0;
+  B200SSL_REQUIRE(labels && preds, "confusion_matrix: null input");
+  const int D = num_classes + (other_bucket ? 1 : 0);
+  long long plane = n_pixels;
+  int planes = 1;
+  long long stride = 0;
+  if (per_image) {
+    B200SSL_REQUIRE(hw > 0 && n_pixels % hw == 0, "confusion_matrix: per_image needs n_pixels %% hw == 0");
+    B200SSL_REQUIRE(n_pixels / hw <= 65535, "confusion_matrix: too many images for per_image mode");
+    plane = hw;
+    planes = (int)(n_pixels / hw);
+    stride = (long long)D * D;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* ucm = reinterpret_cast<unsigned long long*>(cm);
+  unsigned long long* udrop = reinterpret_cast<unsigned long long*>(dropped);
+  const bool has_ign = has_ignore != 0;
+  size_t esz = label_dtype == B200SSL_I64 ? 8 : label_dtype == B200SSL_I32 ? 4 : 1;
+  const bool vec = aligned16(labels) && aligned16(preds) && (planes == 1 || (plane * esz) % 16 == 0);
+  switch (label_dtype) {
+    case B200SSL_I64:
+      return vec ? launch_confusion<long long, 2>(labels, preds, plane, planes, num_classes, D, has_ign, ignore_index, ucm, stride, udrop, s)
+                 : launch_confusion<long long, 1>(labels, preds, plane, planes, num_classes, D, has_ign, ignore_index, ucm, stride, udrop, s);
+    case B200SSL_I32:
+      return vec ? launch_confusion<int, 4>(labels, preds, plane, planes, num_classes, D, has_ign, ignore_index, ucm, stride, udrop, s)
+                 : launch_confusion<int, 1>(labels, preds, plane, planes, num_classes, D, has_ign, ignore_index, ucm, stride, udrop, s);
+    case B200SSL_U8:
+      return vec ? launch_confusion<unsigned char, 16>(labels, preds, plane, planes, num_classes, D, has_ign, ignore_index, ucm, stride, udrop, s)
+                 : launch_confusion<unsigned char, 1>(labels, preds, plane, planes, num_classes, D, has_ign, ignore_index, ucm, stride, udrop, s);
+    default:
+      set_error("confusion_matrix: unknown label dtype %d", label_dtype);
+      return B200SSL_EINVAL;
+  }
+}
+
+int b200ssl_confusion_from_logits(const float* logits, const void* labels, int n_images,
+                                  int num_classes, int64_t hw, int has_ignore, int64_t ignore_index,
+                                  int label_dtype, int per_image, long long* cm, long long* dropped,
+                                  b200ssl_stream_t stream) {
+  using namespace b200ssl;
+  B200SSL_REQUIRE(n_images >= 0 && hw >= 0, "confusion_from_logits: negative extent");
+  B200SSL_REQUIRE(num_classes >= 1 && num_classes <= 4096, "confusion_from_logits: num_classes out of range");
+  B200SSL_REQUIRE(n_images <= 65535, "confusion_from_logits: too many images");
+  B200SSL_REQUIRE(cm != nullptr, "confusion_from_logits: null cm");
+  if (n_images == 0 || hw == 0) return 0;
+  B200SSL_REQUIRE(logits && labels, "confusion_from_logits: null input");
+  const int copies = cm_copies(num_classes);
+  const int D = num_classes;
+  const size_t smem = (size_t)copies * num_classes * num_classes * 4;
+  const long long groups = (hw + 127) / 128;
+  long long bx = (groups + kCmWarps * 4 - 1) / (kCmWarps * 4);
+  long long cap = (long long)kNumSMs * 8 / n_images;
+  if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  const bool vec_ok = aligned16(logits) && (hw % 4 == 0);
+  const long long stride = per_image ? (long long)num_classes * num_classes : 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* ucm = reinterpret_cast<unsigned long long*>(cm);
+  unsigned long long* udrop = reinterpret_cast<unsigned long long*>(dropped);
+#define LAUNCH_LOGITS(T)                                                                       \
+  do {                                                                                         \
+    auto kern = confusion_logits_kernel<T>;                                                    \
+    if (smem > 48 * 1024)                                                                      \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    kern<<<dim3((unsigned)bx, (unsigned)n_images), kCmThreads, smem, s>>>(                     \
+        logits, static_cast<const T*>(labels), hw, num_classes, D, has_ignore != 0, ignore_index, \
+        copies, vec_ok, ucm, stride, udrop);                                                   \
+  } while (0)
+  switch (label_dtype) {
+    case B200SSL_I64: LAUNCH_LOGITS(long long); break;
+    case B200SSL_I32: LAUNCH_LOGITS(int); break;
+    case B200SSL_U8: LAUNCH_LOGITS(unsigned char); break;
+    default:
+      set_error("confusion_from_logits: unknown label dtype %d", label_dtype);
+      return B200SSL_EINVAL;
+  }
+#undef LAUNCH_LOGITS
+  return check_launch("confusion_from_logits");
+}
+
+int b200ssl_dice_from_cm(const long long* cm_per_image, int n_images, float* dice_out,
+                         b200ssl_stream_t stream) {
+  using namespace b200ssl;
+  B200SSL_REQUIRE(n_images >= 0, "dice_from_cm: negative image count");
+  if (n_images == 0) return 0;
+  B200SSL_REQUIRE(cm_per_image && dice_out, "dice_from_cm: null argument");
+  dice_from_cm_kernel<<<(n_images + 127) / 128, 128, 0, (cudaStream_t)stream>>>(cm_per_image, n_images, dice_out);
+  return check_launch("dice_from_cm");
+}
+
+}  // extern "C"

@@ -1,0 +1,181 @@
+// Small reductions around the loss path: channel argmax of the soft one-hot target
+// (losses.py:240 `torch.argmax(target, dim=1)` + the per-sample `tgt.sum() > 0` of :246) and
+// metrics.dice_metric (metrics.py:1-7).
+#include "common.cuh"
+
+namespace b200ssl {
+
+// torch.argmax order: first maximal element wins, NaN counts as the maximum
+__device__ __forceinline__ void argmax_step(float x, int c, float& best, int& arg) {
+  const bool take = (arg < 0) || (x > best) || (x != x && best == best);
+  if (take) { best = x; arg = c; }
+}
+
+template <typename OUT>
+__global__ void __launch_bounds__(256)
+argmax_channels_kernel(const float* __restrict__ x, int C, long long hw, OUT* __restrict__ out,
+                       int* __restrict__ nonzero, bool vec) {
+  const int n = blockIdx.y;
+  const float* __restrict__ xp = x + (long long)n * C * hw;
+  OUT* __restrict__ op = out + (long long)n * hw;
+  int nz = 0;
+  const long long quads = (hw + 3) / 4;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads;
+       q += (long long)gridDim.x * blockDim.x) {
+    const long long first = q * 4;
+    float best[4];
+    int arg[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { best[e] = 0.f; arg[e] = -1; }
+    if (vec && first + 4 <= hw) {
+      for (int c0 = 0; c0 < C; c0 += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (c0 + u < C) v[u] = ld_stream_f4(xp + (long long)(c0 + u) * hw + first);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (c0 + u < C) {
+            argmax_step(v[u].x, c0 + u, best[0], arg[0]);
+            argmax_step(v[u].y, c0 + u, best[1], arg[1]);
+            argmax_step(v[u].z, c0 + u, best[2], arg[2]);
+            argmax_step(v[u].w, c0 + u, best[3], arg[3]);
+          }
+        }
+      }
+    } else {
+      for (int e = 0; e < 4; ++e)
+        if (first + e < hw)
+          for (int c = 0; c < C; ++c) argmax_step(xp[(long long)c * hw + first + e], c, best[e], arg[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (first + e < hw) {
+        op[first + e] = (OUT)arg[e];
+        nz += (arg[e] != 0);
+      }
+    }
+  }
+  if (nonzero) {
+    nz = warp_sum(nz);
+    if (lane_id() == 0 && nz) atomicAdd(nonzero + n, nz);
+  }
+}
+
+constexpr int kDiceThreads = 256;
+
+__global__ void __launch_bounds__(kDiceThreads)
+dice_partial_kernel(const float* __restrict__ x, const float* __restrict__ y, long long chw,
+                    double* __restrict__ partials, bool vec) {
+  const int n = blockIdx.y;
+  const float* __restrict__ xp = x + (long long)n * chw;
+  const float* __restrict__ yp = y + (long long)n * chw;
+  double si = 0.0, sc = 0.0;
+  if (vec) {
+    const long long nv = chw >> 2;
+    for (long long i = (long long)blockIdx.x * kDiceThreads + threadIdx.x; i < nv;
+         i += (long long)gridDim.x * kDiceThreads) {
+      const float4 a = ld_stream_f4(xp + 4 * i), b = ld_stream_f4(yp + 4 * i);
+      si += (double)__fmul_rn(a.x, b.x) + (double)__fmul_rn(a.y, b.y) + (double)__fmul_rn(a.z, b.z) + (double)__fmul_rn(a.w, b.w);
+      sc += (double)__fadd_rn(a.x, b.x) + (double)__fadd_rn(a.y, b.y) + (double)__fadd_rn(a.z, b.z) + (double)__fadd_rn(a.w, b.w);
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * kDiceThreads + threadIdx.x; i < chw;
+         i += (long long)gridDim.x * kDiceThreads) {
+      si += (double)__fmul_rn(xp[i], yp[i]);
+      sc += (double)__fadd_rn(xp[i], yp[i]);
+    }
+  }
+  __shared__ double red[2][kDiceThreads / 32];
+  si = warp_sum(si);
+  sc = warp_sum(sc);
+  if (lane_id() == 0) { red[0][threadIdx.x >> 5] = si; red[1][threadIdx.x >> 5] = sc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < kDiceThreads / 32; ++w) { a += red[0][w]; b += red[1][w]; }
+    partials[((long long)n * gridDim.x + blockIdx.x) * 2 + 0] = a;
+    partials[((long long)n * gridDim.x + blockIdx.x) * 2 + 1] = b;
+  }
+}
+
+__global__ void dice_final_kernel(const double* __restrict__ partials, int per_sample, int n,
+                                  float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a = 0.0, b = 0.0;
+  for (int k = 0; k < per_sample; ++k) {
+    a += partials[((long long)i * per_sample + k) * 2 + 0];
+    b += partials[((long long)i * per_sample + k) * 2 + 1];
+  }
+  const float inter = (float)a, card = (float)b;
+  out[i] = __fdiv_rn(__fadd_rn(__fmul_rn(2.0f, inter), 1.0f), __fadd_rn(card, 1.0f));
+}
+
+static int dice_blocks(int n, long long chw) {
+  long long bx = (chw / 4 + kDiceThreads * 4 - 1) / (kDiceThreads * 4);
+  long long cap = (long long)kNumSMs * 8 / (n > 0 ? n : 1);
+  if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  return (int)bx;
+}
+
+}  // namespace b200ssl
+
+extern "C" {
+
+int b200ssl_argmax_channels(const float* x, int n_images, int n_channels, int64_t hw,
+                            void* labels_out, int out_dtype, int32_t* nonzero_out,
+                            b200ssl_stream_t stream) {
+  using namespace b200ssl;
+  B200SSL_REQUIRE(n_images >= 0 && hw >= 0 && n_channels >= 1, "argmax_channels: bad extents");
+  B200SSL_REQUIRE(n_images <= 65535, "argmax_channels: too many images");
+  B200SSL_REQUIRE(out_dtype == B200SSL_I64 || out_dtype == B200SSL_U8, "argmax_channels: out dtype must be int64 or uint8");
+  B200SSL_REQUIRE(out_dtype != B200SSL_U8 || n_channels <= 256, "argmax_channels: uint8 output needs C <= 256");
+  if (n_images == 0 || hw == 0) return 0;
+  B200SSL_REQUIRE(x && labels_out, "argmax_channels: null argument");
+  const bool vec = aligned16(x) && (hw % 4 == 0);
+  long long bx = ((hw + 3) / 4 + 255) / 256;
+  long long cap = (long long)kNumSMs * 8 / n_images;
+  if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  const dim3 grid((unsigned)bx, (unsigned)n_images);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (out_dtype == B200SSL_I64)
+    argmax_channels_kernel<long long><<<grid, 256, 0, s>>>(x, n_channels, hw, static_cast<long long*>(labels_out), nonzero_out, vec);
+  else
+    argmax_channels_kernel<unsigned char><<<grid, 256, 0, s>>>(x, n_channels, hw, static_cast<unsigned char*>(labels_out), nonzero_out, vec);
+  return check_launch("argmax_channels");
+}
+
+size_t b200ssl_dice_workspace_bytes(int n, int64_t chw) {
+  if (n <= 0 || chw <= 0) return 0;
+  return (size_t)n * b200ssl::dice_blocks(n, chw) * 2 * sizeof(double);
+}
+
+int b200ssl_dice_metric(const float* input, const float* target, int n, int64_t chw,
+                        float* dice_out, void* workspace, size_t workspace_bytes,
+                        b200ssl_stream_t stream) {
+  using namespace b200ssl;
+  B200SSL_REQUIRE(n >= 0 && chw >= 0, "dice_metric: bad extents");
+  B200SSL_REQUIRE(n <= 65535, "dice_metric: too many samples");
+  if (n == 0) return 0;
+  B200SSL_REQUIRE(input && target && dice_out, "dice_metric: null argument");
+  const int bx = dice_blocks(n, chw);
+  const size_t need = (size_t)n * bx * 2 * sizeof(double);
+  if (!workspace || workspace_bytes < need) {
+    set_error("dice_metric: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return B200SSL_EWORKSPACE;
+  }
+  const bool vec = aligned16(input) && aligned16(target) && (chw % 4 == 0);
+  cudaStream_t s = (cudaStream_t)stream;
+  dice_partial_kernel<<<dim3((unsigned)bx, (unsigned)n), kDiceThreads, 0, s>>>(
+      input, target, chw, static_cast<double*>(workspace), vec);
+  int rc = check_launch("dice partial");
+  if (rc) return rc;
+  dice_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(static_cast<const double*>(workspace), bx, n, dice_out);
+  return check_launch("dice final");
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// Fused CowMix mixing: images and predictions are mixed with the same mask in one pass.
+// Reference semantics: cowmix.py:72-73, called twice per step (train.py:82 and :84-86); each call
+// is 4 ATen kernels with 3 temporaries there (~28 B/element moved), here 12 B/element + the mask
+// once per pixel.
+//
+// Roofline: HBM-bound, 4*(3*c0 + 3*c1 + 1) bytes per pixel.
+#include "common.cuh"
+
+namespace b200ssl {
+
+constexpr int kMixThreads = 256;
+constexpr int kMixChanUnroll = 4;
+
+// RN(RN(a*m) + RN(b*RN(1-m))): the exact op sequence of `a*mask + b*(1.-mask)`; no FMA contraction.
+__device__ __forceinline__ float mix_one(float a, float b, float m, float om) {
+  return __fadd_rn(__fmul_rn(a, m), __fmul_rn(b, om));
+}
+
+template <int VEC>
+struct Pack;
+template <>
+struct Pack<4> {
+  float4 v;
+  __device__ __forceinline__ void load(const float* p) { v = ld_stream_f4(p); }
+  __device__ __forceinline__ void store(float* p) const { st_stream_f4(p, v); }
+  __device__ __forceinline__ float& at(int i) { return (&v.x)[i]; }
+};
+template <>
+struct Pack<1> {
+  float v;
+  __device__ __forceinline__ void load(const float* p) { v = ld_stream_f1(p); }
+  __device__ __forceinline__ void store(float* p) const { *p = v; }
+  __device__ __forceinline__ float& at(int) { return v; }
+};
+
+template <int VEC, bool CHANNEL_MASK>
+__device__ __forceinline__ void mix_tensor(const float* __restrict__ a, const float* __restrict__ b,
+                                           float* __restrict__ out, int c, long long n_idx,
+                                           long long off, long long hw, Pack<VEC> m, Pack<VEC> om,
+                                           const float* __restrict__ mask) {
+  const long long base = n_idx * c * hw + off;
+  for (int j0 = 0; j0 < c; j0 += kMixChanUnroll) {
+    Pack<VEC> av[kMixChanUnroll], bv[kMixChanUnroll], mv[kMixChanUnroll];
+#pragma unroll
+    for (int u = 0; u < kMixChanUnroll; ++u) {
+      if (j0 + u < c) {
+        av[u].load(a + base + (long long)(j0 + u) * hw);
+        bv[u].load(b + base + (long long)(j0 + u) * hw);
+        if (CHANNEL_MASK) mv[u].load(mask + base + (long long)(j0 + u) * hw);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kMixChanUnroll; ++u) {
+      if (j0 + u < c) {
+        Pack<VEC> o;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          if (CHANNEL_MASK) {
+            const float mm = mv[u].at(e);
+            o.at(e) = mix_one(av[u].at(e), bv[u].at(e), mm, __fsub_rn(1.0f, mm));
+          } else {
+            o.at(e) = mix_one(av[u].at(e), bv[u].at(e), m.at(e), om.at(e));
+          }
+        }
+        o.store(out + base + (long long)(j0 + u) * hw);
+      }
+    }
+  }
+}
+
+template <int VEC, bool CHANNEL_MASK>
+__global__ void __launch_bounds__(kMixThreads)
+mix2_kernel(const float* __restrict__ a0, const float* __restrict__ b0, float* __restrict__ out0,
+            int c0, const float* __restrict__ a1, const float* __restrict__ b1,
+            float* __restrict__ out1, int c1, const float* __restrict__ mask, long long n,
+            long long hw) {
+  const long long per_img = hw / VEC;
+  const long long total = n * per_img;
+  for (long long q = (long long)blockIdx.x * kMixThreads + threadIdx.x; q < total;
+       q += (long long)gridDim.x * kMixThreads) {
+    const long long n_idx = q / per_img;
+    const long long off = (q - n_idx * per_img) * VEC;
+    Pack<VEC> m, om;
+    if (!CHANNEL_MASK) {
+      m.load(mask + n_idx * hw + off);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) om.at(e) = __fsub_rn(1.0f, m.at(e));
+    }
+    mix_tensor<VEC, CHANNEL_MASK>(a0, b0, out0, c0, n_idx, off, hw, m, om, mask);
+    if (c1 > 0) mix_tensor<VEC, false>(a1, b1, out1, c1, n_idx, off, hw, m, om, mask);
+  }
+}
+
+}  // namespace b200ssl
+
+extern "C" int b200ssl_mix2(const float* a0, const float* b0, float* out0, int c0, const float* a1,
+                            const float* b1, float* out1, int c1, const float* mask,
+                            int mask_channels, int64_t n, int64_t hw, b200ssl_stream_t stream) {
+  using namespace b200ssl;
+  B200SSL_REQUIRE(n >= 0 && hw >= 0 && c0 >= 0 && c1 >= 0, "mix2: negative extent");
+  if (n == 0 || hw == 0 || (c0 == 0 && c1 == 0)) return 0;
+  B200SSL_REQUIRE(mask != nullptr, "mix2: null mask");
+  B200SSL_REQUIRE(c0 == 0 || (a0 && b0 && out0), "mix2: null tensor 0");
+  B200SSL_REQUIRE(c1 == 0 || (a1 && b1 && out1), "mix2: null tensor 1");
+  const bool chan_mask = (mask_channels != 1);
+  B200SSL_REQUIRE(!chan_mask || (mask_channels == c0 && c1 == 0),
+                  "mix2: per-channel mask needs mask_channels == c0 and no second tensor");
+  bool vec = (hw % 4 == 0) && aligned16(mask);
+  if (c0) vec = vec && aligned16(a0) && aligned16(b0) && aligned16(out0);
+  if (c1) vec = vec && aligned16(a1) && aligned16(b1) && aligned16(out1);
+  const long long work = (long long)n * (vec ? hw / 4 : hw);
+  long long blocks = (work + kMixThreads - 1) / kMixThreads;
+  const long long cap = (long long)kNumSMs * 8 * 16;  // grid-stride beyond 16 waves of 8 CTAs/SM
+  if (blocks > cap) blocks = cap;
+  cudaStream_t s = (cudaStream_t)stream;
+#define LAUNCH(V, CM) \
+  mix2_kernel<V, CM><<<(int)blocks, kMixThreads, 0, s>>>(a0, b0, out0, c0, a1, b1, out1, c1, mask, n, hw)
+  if (vec) {
+    if (chan_mask) LAUNCH(4, true); else LAUNCH(4, false);
+  } else {
+    if (chan_mask) LAUNCH(1, true); else LAUNCH(1, false);
+  }
+#undef LAUNCH
+  return check_launch("mix2");
+}

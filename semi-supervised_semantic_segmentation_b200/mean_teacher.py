@@ -1,0 +1,100 @@
+"""Drop-in for the reference's mean_teacher.py.
+
+    reference mean_teacher.py:5-18   update_ema_variables(model, ema_model, alpha)
+    reference mean_teacher.py:20-22  detach_model_parameters(model)
+
+The reference issues `mul_` + `add_` per parameter tensor (2 launches x hundreds of tensors); here
+all parameters are updated by ONE launch that walks a device-resident chunk table.  The table is
+rebuilt only when a data pointer changes (checkpoint loads copy in place, so it normally never does).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, stream_ptr
+
+_tables = {}
+
+
+def _dense_like(a, b):
+    return (a.stride() == b.stride() and a.shape == b.shape and
+            (a.is_contiguous() or a.is_contiguous(memory_format=torch.channels_last)
+             if a.dim() == 4 else a.is_contiguous()))
+
+
+def _build_table(ema_params, params, device):
+    n = len(params)
+    numels = (C.c_int64 * n)(*[p.numel() for p in params])
+    entries = lib.b200ssl_ema_table_entries(numels, n)
+    if entries < 0:
+        check(int(entries), "ema_table_entries")
+    ema_ptrs = (C.c_void_p * n)(*[e.data_ptr() for e in ema_params])
+    par_ptrs = (C.c_void_p * n)(*[p.data_ptr() for p in params])
+    host = torch.empty(max(int(entries), 1) * C.sizeof(_lib.EmaChunk), dtype=torch.uint8, pin_memory=True)
+    written = lib.b200ssl_ema_build_table_host(ema_ptrs, par_ptrs, numels, n, host.data_ptr(), int(entries))
+    if written < 0:
+        check(int(written), "ema_build_table_host")
+    return host.to(device, non_blocking=True), int(written), host
+
+
+class EmaUpdater:
+    """Caches the chunk table for one (student, teacher) pair."""
+
+    def __init__(self):
+        self._key = None
+        self._table = None
+        self._entries = 0
+        self._host = None  # keeps the pinned staging buffer alive until the copy has run
+
+    def __call__(self, ema_params, params, alpha):
+        if len(ema_params) != len(params):
+            # zip() in the reference silently truncates; identically-built models never differ
+            n = min(len(ema_params), len(params))
+            ema_params, params = ema_params[:n], params[:n]
+        if not params:
+            return
+        device = params[0].device
+        for e, p in zip(ema_params, params):
+            if not (e.is_cuda and p.is_cuda):
+                raise RuntimeError("b200ssl.mean_teacher: parameters must live on a CUDA device "
+                                   "(no CPU fallback)")
+            if e.device != device or p.device != device:
+                raise RuntimeError("b200ssl.mean_teacher: all parameters must be on one device")
+            if e.dtype != torch.float32 or p.dtype != torch.float32:
+                raise TypeError("b200ssl.mean_teacher: only float32 parameters are supported")
+            if not _dense_like(e, p):
+                raise ValueError("b200ssl.mean_teacher: teacher/student parameters must be dense "
+                                 "with identical shapes and strides")
+        key = (device, tuple((e.data_ptr(), p.data_ptr(), p.numel()) for e, p in zip(ema_params, params)))
+        if key != self._key:
+            self._table, self._entries, self._host = _build_table(ema_params, params, device)
+            self._key = key
+        with torch.cuda.device(device):
+            check(lib.b200ssl_ema_multi(self._table.data_ptr(), self._entries, float(alpha),
+                                        stream_ptr(device)), "ema_multi")
+
+
+_default_updaters = {}
+
+
+def update_ema_variables(model, ema_model, alpha):
+    with torch.no_grad():
+        # Use the true average until the exponential average is more correct
+        # alpha = min(1 - 1 / (global_step + 1), alpha)
+        ema_params = [p.data for p in ema_model.parameters()]
+        params = [p.data for p in model.parameters()]
+        key = (id(model), id(ema_model))
+        upd = _default_updaters.get(key)
+        if upd is None:
+            upd = _default_updaters[key] = EmaUpdater()
+        upd(ema_params, params, alpha)
+
+        # mean_teacher.py:13-18: both branches re-point the teacher's buffer at the student's storage
+        for ema_buffer, buffer in zip(ema_model.buffers(), model.buffers()):
+            ema_buffer.data = buffer.data
+
+
+def detach_model_parameters(model):
+    for param in model.parameters():
+        param.detach_()
