@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- loss-path throughput (CowMix mask + fused mix + Lovasz fwd/bwd + EMA + confusion matrix).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" is one pass of the semi-supervised loss path over one synthetic batch per GPU
+(BASELINE.json configs[1]: 16 x 512 x 512, 2 classes, unet+mobilenetv2 parameter set).  Rank 0 prints
+ONE JSON line.  See DESIGN.md "Measurement" for the definition of every key.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "loss-path Mpixels/s (CowMix+Lovasz fwd/bwd+EMA+cm)"
+UNIT = "Mpixels/s"
+WORKLOAD = dict(name="configs[1]: unet 2-class, batch 16x512x512 per GPU", n=16, c=2, h=512, w=512,
+                params="unet_mnv2_c2", p_range=(0.45, 0.55), sigma_range=(8, 32), alpha=0.99)
+REF_SAMPLE_IMAGES = 4       # --impl reference: images per step (bounded sample of the 16-image batch)
+
+
+def load_param_shapes(key):
+    with open(os.path.join(ROOT, "tests", "golden", "param_shapes.json")) as f:
+        return json.load(f)[key]["shapes"]
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def coherent_labels(n, c, h, w, device, gen):
+    """Spatially coherent label maps: argmax over C channels of blurred noise."""
+    x = torch.randn(n, c, h, w, device=device, generator=gen)
+    for _ in range(3):
+        x = torch.nn.functional.avg_pool2d(x, 17, 1, 8)
+    return x.argmax(1)
+
+
+def make_inputs(device, rank, n=None):
+    W = WORKLOAD
+    n = W["n"] if n is None else n
+    gen = torch.Generator(device=device).manual_seed(1234 + rank)
+    c, h, w = W["c"], W["h"], W["w"]
+    d = {
+        "image_a": torch.rand(n, 3, h, w, device=device, generator=gen),
+        "image_b": torch.rand(n, 3, h, w, device=device, generator=gen),
+        "teacher_a": torch.randn(n, c, h, w, device=device, generator=gen) * 3,
+        "teacher_b": torch.randn(n, c, h, w, device=device, generator=gen) * 3,
+        "scores": torch.randn(n, c, h, w, device=device, generator=gen) * 3,
+    }
+    labels = coherent_labels(n, c, h, w, device, gen)
+    d["target"] = torch.nn.functional.one_hot(labels, c).permute(0, 3, 1, 2).float().contiguous()
+    shapes = load_param_shapes(W["params"])
+    d["params"] = [torch.randn(s, device=device, generator=gen) for s in shapes]
+    d["ema_params"] = [torch.randn(s, device=device, generator=gen) for s in shapes]
+    return d
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            time.sleep(0.25)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.1)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if not sm:
+            return None
+        load = sorted(x for x in sm if x >= 0.5 * max(sm)) or sorted(sm)
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(P, C, n_params, label_bytes=1):
+    """Compulsory bytes per launch of each kernel for P pixels (DESIGN.md 'Kernels'); binary mode:
+    one Lovasz segment per image, P keys in total."""
+    elems = P * C
+    return {
+        "cowmix_conv_pass1": 8 * P, "cowmix_conv_pass2": 8 * P, "cowmix_threshold": 8 * P,
+        "mix2": 4 * (3 * 3 + 3 * C + 1) * P,
+        "argmax_channels": (4 * C + label_bytes) * P,
+        "lovasz_keybuild": (4 + label_bytes + 8) * P,
+        "lovasz_sort_pass0": 16 * P, "lovasz_sort_pass1": 16 * P, "lovasz_sort_pass2": 16 * P,
+        "lovasz_rank_grad_pass3": 12 * P,
+        "lovasz_backward": 8 * elems,
+        "ema_multi": 12 * n_params,
+        "confusion_from_logits": (4 * C + label_bytes) * P,
+    }
+
+
+def step_algorithmic_bytes(P, C, n_params):
+    """P*(72+20C) + 12*n_params (mask 8, mix 40+12C, Lovasz 8C+8, CM 16 per pixel)."""
+    return P * (72 + 20 * C) + 12 * n_params
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import b200ssl
+    from b200ssl import _lib
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    W = WORKLOAD
+    inp = make_inputs(device, rank)
+    P = W["n"] * W["h"] * W["w"]
+    n_params = sum(p.numel() for p in inp["params"])
+    step = b200ssl.LossPathStep(num_classes=W["c"], mask_proportion_range=W["p_range"],
+                                sigma_range=W["sigma_range"], ema_alpha=W["alpha"], mode="binary")
+    reducer = b200ssl.utils.StepReducer(W["c"], 1, device)
+    torch.manual_seed(0)            # the reference seeds every rank with 0 (distributed_trainer.py:17)
+
+    def one_step():
+        out = step(inp["image_a"], inp["image_b"], inp["teacher_a"], inp["teacher_b"], inp["scores"],
+                   inp["target"], inp["params"], inp["ema_params"])
+        if world > 1:
+            reducer.all_reduce(out["cm"], [out["loss"]])
+        return out
+
+    def sync_all():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    sync_all()
+
+    # ---- timed region: K steps, device-resident inputs ----
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        out = one_step()
+    e1.record()
+    sync_all()
+    launches = _lib.launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    clock_info = clocks.stop() if rank == 0 else None
+
+    # ---- per-kernel CUDA-event timing over K more steps (explains the number above) ----
+    _lib.kernel_times(True)
+    for _ in range(args.steps):
+        one_step()
+    torch.cuda.synchronize(device)
+    ktimes = _lib.kernel_times()
+    _lib.kernel_times(False)
+
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of loss + confusion matrix ----
+    names = ["image_a", "image_b", "teacher_a", "teacher_b", "scores", "target"]
+    host = {k: inp[k].cpu().pin_memory() for k in names}
+    dev_in = {k: torch.empty_like(inp[k]) for k in names}
+    h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in names)
+    res_host = torch.empty(1 + W["c"] * W["c"], dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        for k in names:
+            dev_in[k].copy_(host[k], non_blocking=True)
+        o = step(dev_in["image_a"], dev_in["image_b"], dev_in["teacher_a"], dev_in["teacher_b"],
+                 dev_in["scores"], dev_in["target"], inp["params"], inp["ema_params"])
+        if world > 1:
+            cm, sc = reducer.all_reduce(o["cm"], [o["loss"]])
+            packed = torch.cat([sc.reshape(-1)[:1], cm.reshape(-1).to(torch.float64)])
+        else:
+            packed = torch.cat([o["loss"].reshape(1).to(torch.float64), o["cm"].reshape(-1).to(torch.float64)])
+        res_host.copy_(packed, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()     # the caller reads the loss every step
+        return res_host
+
+    for _ in range(3):
+        e2e_step()
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e3.record()
+    sync_all()
+    ms_e2e = torch.tensor([e2.elapsed_time(e3)], device=device, dtype=torch.float64)
+
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(ms), float(ms_e2e)
+    if rank != 0:
+        return None
+
+    peak, peak_src = measured_peak()
+    value = world * P * args.steps / (ms * 1e-3) / 1e6
+    e2e_value = world * P * args.steps / (ms_e2e * 1e-3) / 1e6
+    abytes = algorithmic_bytes(P, W["c"], n_params)
+    stages = {}
+    for name, (cnt, total_ms, min_ms) in ktimes.items():
+        avg = total_ms / max(cnt, 1)
+        b = abytes.get(name)
+        stages[name] = {"launches_per_step": cnt / args.steps, "avg_ms": round(avg, 5),
+                        "alg_GB": None if b is None else round(b / 1e9, 5),
+                        "GBps": None if b is None or avg <= 0 else round(b / 1e9 / (avg * 1e-3), 1)}
+    per_step_kernel_ms = sum(t for (_, t, _) in ktimes.values()) / args.steps
+    top = max((k for k in ktimes if k in abytes), key=lambda k: ktimes[k][1])
+    top_avg_ms = ktimes[top][1] / ktimes[top][0]
+    achieved = abytes[top] / 1e9 / (top_avg_ms * 1e-3)
+    K_taps = None
+    roof = {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+            "avg_launch_ms": round(top_avg_ms, 5),
+            "share_of_kernel_time": round(ktimes[top][1] / args.steps / per_step_kernel_ms, 4),
+            "stages": stages,
+            "step": {"alg_GB": round(step_algorithmic_bytes(P, W["c"], n_params) / 1e9, 4),
+                     "GBps": round(step_algorithmic_bytes(P, W["c"], n_params) / 1e9 / (ms / args.steps * 1e-3), 1),
+                     "frac": round(step_algorithmic_bytes(P, W["c"], n_params) / 1e9 / (ms / args.steps * 1e-3) / peak, 4),
+                     "kernel_ms_per_step": round(per_step_kernel_ms, 4)}}
+    if top.startswith("cowmix_conv"):
+        roof["note"] = ("this kernel is fp32-FMA bound (2K FMA per pixel, K up to 193), not HBM bound; "
+                        "see roofline.stages and DESIGN.md for its FMA-rate fraction")
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": W["name"], "pixels_per_gpu_step": P, "classes": W["c"],
+                   "ema_params": n_params, "ema_tensors": len(inp["params"]),
+                   "lovasz": "losses.binary_lovasz_loss_with_logits (per image, class 1)",
+                   "sigma_range": list(W["sigma_range"]), "parallelism": f"dp{world}",
+                   "l2": "no flush: the 234 MB of step inputs (+268 MB outputs/workspace) exceed the 126 MB L2"},
+        "clocks": clock_info,
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": res_host.numel() * 8, "ms_per_step": round(ms_e2e / args.steps, 4)},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+    }
+    if world == 1:
+        line["cpu_baseline"] = cpu_baseline(inp, full=True, steps=2, warmup=1)
+    return line
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_inputs(inp, n_images):
+    keys = ["image_a", "image_b", "teacher_a", "teacher_b", "scores", "target"]
+    d = {k: inp[k][:n_images].cpu() for k in keys}
+    d["params"] = [p.cpu() for p in inp["params"]]
+    d["ema_params"] = [p.cpu().clone() for p in inp["ema_params"]]
+    return d
+
+
+def cpu_step(d):
+    from oracle import torch_port
+    W = WORKLOAD
+    return torch_port.loss_path_step(d["image_a"], d["image_b"], d["teacher_a"], d["teacher_b"], d["scores"],
+                                     d["target"], d["params"], d["ema_params"], mode="binary",
+                                     mask_proportion_range=W["p_range"], sigma_range=W["sigma_range"],
+                                     alpha=W["alpha"], num_classes=W["c"])
+
+
+def cpu_baseline(inp, full, steps, warmup):
+    """The oracle's torch port (the reference's ATen op sequence) on this host's cores."""
+    W = WORKLOAD
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_img = W["n"] if full else REF_SAMPLE_IMAGES
+    d = cpu_inputs(inp, n_img)
+    torch.manual_seed(0)
+    for _ in range(warmup):
+        cpu_step(d)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(d)
+    dt = (time.perf_counter() - t0) / steps
+    pix = n_img * W["h"] * W["w"]
+    return {"value": round(pix / dt / 1e6, 3), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_img} of {W['n']} images x {W['h']}x{W['w']} per step, full EMA parameter set, "
+                      f"{steps} timed steps after {warmup} warm-up; oracle/torch_port.py (torch CPU ops, "
+                      f"{torch.get_num_threads()} threads)",
+            "ms_per_step": round(dt * 1e3, 2)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port: the reference is
+    Python and /root/reference does not exist on the GPU box), rank 0 only."""
+    if rank != 0:
+        return None
+    W = WORKLOAD
+    inp = make_inputs(torch.device("cpu"), 0, n=REF_SAMPLE_IMAGES)
+    base = cpu_baseline(inp, full=False, steps=max(args.steps, 1), warmup=max(args.warmup, 1))
+    return {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": W["name"], "classes": W["c"], "sigma_range": list(W["sigma_range"]),
+                   "sample_images_per_step": REF_SAMPLE_IMAGES},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        line = run_reference(args, rank, world)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return 0
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        line = run_b200(args, rank, world, local_rank)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+    finally:
+        if world > 1 and dist.is_initialized():
+            dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -51,6 +51,15 @@ const char* b200ssl_last_error(void);
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
 long long b200ssl_launch_count(void);
 
+/* Optional per-kernel timing for bench.py's roofline line.  While enabled, every kernel launch of
+ * this library is bracketed by two CUDA events recorded on the launch stream.
+ * b200ssl_prof_report waits for the recorded events (the only call of the library that
+ * synchronises), writes one line per kernel name -- "<name> <launches> <total_ms> <min_ms>\n" --
+ * into buf (NUL terminated, truncated to capacity), forgets the records and returns the untruncated
+ * length. */
+void b200ssl_prof_enable(int on);
+long long b200ssl_prof_report(char* buf, size_t capacity);
+
 /* ---------------------------------------------------------------------------------------------
  * Mean-teacher EMA over all parameter tensors in ONE launch.
  * Replaces mean_teacher.update_ema_variables, reference mean_teacher.py:10-11

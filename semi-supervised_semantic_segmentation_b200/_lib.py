@@ -42,6 +42,8 @@ SIGNATURES = {
     "b200ssl_version": (_i, []),
     "b200ssl_last_error": (C.c_char_p, []),
     "b200ssl_launch_count": (C.c_longlong, []),
+    "b200ssl_prof_enable": (None, [_i]),
+    "b200ssl_prof_report": (C.c_longlong, [C.c_char_p, _sz]),
     "b200ssl_ema_table_entries": (_i64, [_vp, _i]),
     "b200ssl_ema_build_table_host": (_i64, [_vp, _vp, _vp, _i, _vp, _i64]),
     "b200ssl_ema_multi": (_i, [_vp, _i64, _d, _vp]),
@@ -92,6 +94,21 @@ def check(rc, what=""):
 
 def launch_count():
     return int(lib.b200ssl_launch_count())
+
+
+def kernel_times(enable=None):
+    """enable=True/False switches per-kernel event timing; enable=None collects
+    {kernel name: (launches, total_ms, min_ms)} since the last collection (synchronises)."""
+    if enable is not None:
+        lib.b200ssl_prof_enable(1 if enable else 0)
+        return None
+    buf = C.create_string_buffer(1 << 16)
+    lib.b200ssl_prof_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, total, mn = line.split()
+        out[name] = (int(n), float(total), float(mn))
+    return out
 
 
 def stream_ptr(device=None):

@@ -16,8 +16,13 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multi
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// optional per-kernel timing (b200ssl_prof_enable): prof_begin records a start event on the stream,
+// check_launch / prof_end the matching stop event; both are a single flag test when profiling is off
+void prof_begin(const char* name, cudaStream_t stream);
+void prof_end();
 
 inline int check_launch(const char* what) {
+  prof_end();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));

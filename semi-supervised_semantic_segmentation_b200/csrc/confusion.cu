@@ -257,6 +257,7 @@ static int launch_confusion(const void* labels, const void* preds, long long pla
   if (bx < 1) bx = 1;
   auto kern = confusion_kernel<T, ELEMS>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  prof_begin("confusion_matrix", s);
   kern<<<dim3((unsigned)bx, (unsigned)planes), kCmThreads, smem, s>>>(
       static_cast<const T*>(labels), static_cast<const T*>(preds), plane_pixels, C, D, has_ignore,
       ignore, copies, cm, cm_stride, dropped);
@@ -343,6 +344,7 @@ int b200ssl_confusion_from_logits(const float* logits, const void* labels, int n
         logits, static_cast<const T*>(labels), hw, num_classes, D, has_ignore != 0, ignore_index, \
         copies, vec_ok, ucm, stride, udrop);                                                   \
   } while (0)
+  prof_begin("confusion_from_logits", s);
   switch (label_dtype) {
     case B200SSL_I64: LAUNCH_LOGITS(long long); break;
     case B200SSL_I32: LAUNCH_LOGITS(int); break;
@@ -361,6 +363,7 @@ int b200ssl_dice_from_cm(const long long* cm_per_image, int n_images, float* dic
   B200SSL_REQUIRE(n_images >= 0, "dice_from_cm: negative image count");
   if (n_images == 0) return 0;
   B200SSL_REQUIRE(cm_per_image && dice_out, "dice_from_cm: null argument");
+  prof_begin("dice_from_cm", (cudaStream_t)stream);
   dice_from_cm_kernel<<<(n_images + 127) / 128, 128, 0, (cudaStream_t)stream>>>(cm_per_image, n_images, dice_out);
   return check_launch("dice_from_cm");
 }

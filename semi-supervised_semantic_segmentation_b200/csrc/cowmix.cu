@@ -262,6 +262,7 @@ int b200ssl_cowmix_mask(const float* noise, const float* taps, int K, const floa
   {
     const ConvGrid g = conv_grid(n, h, w);
     const bool vec2 = (w % 2 == 0) && ((reinterpret_cast<uintptr_t>(noise) & 7u) == 0);
+    prof_begin("cowmix_conv_pass1", s);
     if (vec2)
       conv_slow_axis_transposed<true, false><<<g.grid, kConvThreads, smem, s>>>(noise, Vt, taps, K, h, w, nullptr);
     else
@@ -273,6 +274,7 @@ int b200ssl_cowmix_mask(const float* noise, const float* taps, int K, const floa
   const ConvGrid g2 = conv_grid(n, w, h);
   {
     const bool vec2 = (h % 2 == 0);
+    prof_begin("cowmix_conv_pass2", s);
     if (vec2)
       conv_slow_axis_transposed<true, true><<<g2.grid, kConvThreads, smem, s>>>(Vt, S, taps, K, w, h, partials);
     else
@@ -287,6 +289,7 @@ int b200ssl_cowmix_mask(const float* noise, const float* taps, int K, const floa
     if (cap < 1) cap = 1;
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
+    prof_begin("cowmix_threshold", s);
     cowmix_threshold_kernel<<<dim3((unsigned)bx, (unsigned)n), 256, 0, s>>>(
         S, thr_factor, partials, g2.partials_per_sample, (long long)plane, mask_out, vec);
     return check_launch("cowmix threshold");

@@ -128,6 +128,7 @@ int b200ssl_ema_multi(const b200ssl_ema_chunk* table_dev, int64_t n_entries, dou
   const float b = (float)(1.0 - alpha);  // add_(alpha=1.-alpha): evaluated in double, then fp32
   const long long max_grid = (long long)kNumSMs * 8;
   const int grid = (int)(n_entries < max_grid ? n_entries : max_grid);
+  prof_begin("ema_multi", (cudaStream_t)stream);
   ema_multi_kernel<<<grid, kEmaThreads, 0, (cudaStream_t)stream>>>(table_dev, n_entries, a, b);
   return check_launch("ema_multi");
 }

@@ -142,6 +142,7 @@ int b200ssl_argmax_channels(const float* x, int n_images, int n_channels, int64_
   if (bx > cap) bx = cap;
   const dim3 grid((unsigned)bx, (unsigned)n_images);
   cudaStream_t s = (cudaStream_t)stream;
+  prof_begin("argmax_channels", s);
   if (out_dtype == B200SSL_I64)
     argmax_channels_kernel<long long><<<grid, 256, 0, s>>>(x, n_channels, hw, static_cast<long long*>(labels_out), nonzero_out, vec);
   else
@@ -170,10 +171,12 @@ int b200ssl_dice_metric(const float* input, const float* target, int n, int64_t 
   }
   const bool vec = aligned16(input) && aligned16(target) && (chw % 4 == 0);
   cudaStream_t s = (cudaStream_t)stream;
+  prof_begin("dice_partial", s);
   dice_partial_kernel<<<dim3((unsigned)bx, (unsigned)n), kDiceThreads, 0, s>>>(
       input, target, chw, static_cast<double*>(workspace), vec);
   int rc = check_launch("dice partial");
   if (rc) return rc;
+  prof_begin("dice_final", s);
   dice_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(static_cast<const double*>(workspace), bx, n, dice_out);
   return check_launch("dice final");
 }

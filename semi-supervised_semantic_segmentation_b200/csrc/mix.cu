@@ -115,6 +115,7 @@ extern "C" int b200ssl_mix2(const float* a0, const float* b0, float* out0, int c
   cudaStream_t s = (cudaStream_t)stream;
 #define LAUNCH(V, CM) \
   mix2_kernel<V, CM><<<(int)blocks, kMixThreads, 0, s>>>(a0, b0, out0, c0, a1, b1, out1, c1, mask, n, hw)
+  prof_begin("mix2", s);
   if (vec) {
     if (chan_mask) LAUNCH(4, true); else LAUNCH(4, false);
   } else {
