@@ -81,13 +81,14 @@ class ClockSampler:
         self.path = None
 
     def start(self):
+        if os.environ.get("B200SSL_BENCH_NO_CLOCKS"):
+            return
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
                  "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-            time.sleep(0.25)
         except Exception:
             self.proc = None
 
@@ -175,14 +176,23 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize(device)
 
-    for _ in range(max(args.warmup, 3)):
-        one_step()
-    sync_all()
-
-    # ---- timed region: K steps, device-resident inputs ----
+    # The clock sampler (nvidia-smi -lms) is started BEFORE the warm-up and the warm-up runs for at
+    # least ~1.2 s of GPU load: nvidia-smi's own start-up disturbs kernel launches for a few hundred
+    # milliseconds (measured: 1.45 vs 0.63 ms/step on a 20-step region), and the clocks need samples
+    # taken under load.  Everything from here to clocks.stop() keeps the GPU busy.
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    t_w = time.perf_counter()
+    n_w = 0
+    while n_w < max(args.warmup, 3) or (time.perf_counter() - t_w) < 1.2:
+        one_step()
+        n_w += 1
+        if n_w % 16 == 0:
+            torch.cuda.synchronize(device)
+    sync_all()
+
+    # ---- timed region: K steps, device-resident inputs ----
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
@@ -196,8 +206,9 @@ def run_b200(args, rank, world, local_rank):
     clock_info = clocks.stop() if rank == 0 else None
 
     # ---- per-kernel CUDA-event timing over K more steps (explains the number above) ----
+    prof_steps = min(args.steps, 20)
     _lib.kernel_times(True)
-    for _ in range(args.steps):
+    for _ in range(prof_steps):
         one_step()
     torch.cuda.synchronize(device)
     ktimes = _lib.kernel_times()
@@ -250,10 +261,10 @@ def run_b200(args, rank, world, local_rank):
     for name, (cnt, total_ms, min_ms) in ktimes.items():
         avg = total_ms / max(cnt, 1)
         b = abytes.get(name)
-        stages[name] = {"launches_per_step": cnt / args.steps, "avg_ms": round(avg, 5),
+        stages[name] = {"launches_per_step": cnt / prof_steps, "avg_ms": round(avg, 5),
                         "alg_GB": None if b is None else round(b / 1e9, 5),
                         "GBps": None if b is None or avg <= 0 else round(b / 1e9 / (avg * 1e-3), 1)}
-    per_step_kernel_ms = sum(t for (_, t, _) in ktimes.values()) / args.steps
+    per_step_kernel_ms = sum(t for (_, t, _) in ktimes.values()) / prof_steps
     top = max((k for k in ktimes if k in abytes), key=lambda k: ktimes[k][1])
     top_avg_ms = ktimes[top][1] / ktimes[top][0]
     achieved = abytes[top] / 1e9 / (top_avg_ms * 1e-3)
@@ -261,7 +272,7 @@ def run_b200(args, rank, world, local_rank):
     roof = {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
             "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
             "avg_launch_ms": round(top_avg_ms, 5),
-            "share_of_kernel_time": round(ktimes[top][1] / args.steps / per_step_kernel_ms, 4),
+            "share_of_kernel_time": round(ktimes[top][1] / prof_steps / per_step_kernel_ms, 4),
             "stages": stages,
             "step": {"alg_GB": round(step_algorithmic_bytes(P, W["c"], n_params) / 1e9, 4),
                      "GBps": round(step_algorithmic_bytes(P, W["c"], n_params) / 1e9 / (ms / args.steps * 1e-3), 1),
@@ -272,7 +283,7 @@ def run_b200(args, rank, world, local_rank):
                         "see roofline.stages and DESIGN.md for its FMA-rate fraction")
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        "warmup": n_w, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": W["name"], "pixels_per_gpu_step": P, "classes": W["c"],
                    "ema_params": n_params, "ema_tensors": len(inp["params"]),
@@ -308,12 +319,12 @@ def cpu_step(d):
                                      alpha=W["alpha"], num_classes=W["c"])
 
 
-def cpu_baseline(inp, full, steps, warmup):
+def cpu_baseline(inp, full, steps, warmup, n_images=None):
     """The oracle's torch port (the reference's ATen op sequence) on this host's cores."""
     W = WORKLOAD
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n_img = W["n"] if full else REF_SAMPLE_IMAGES
+    n_img = W["n"] if full else (n_images or REF_SAMPLE_IMAGES)
     d = cpu_inputs(inp, n_img)
     torch.manual_seed(0)
     for _ in range(warmup):
@@ -337,13 +348,22 @@ def run_reference(args, rank, world):
         return None
     W = WORKLOAD
     inp = make_inputs(torch.device("cpu"), 0, n=REF_SAMPLE_IMAGES)
-    base = cpu_baseline(inp, full=False, steps=max(args.steps, 1), warmup=max(args.warmup, 1))
+    # bounded sample: shrink the per-step image count so that (K+W) steps end within ~3 minutes
+    torch.set_num_threads(os.cpu_count() or 1)
+    probe = cpu_inputs(inp, 1)
+    cpu_step(probe)
+    t0 = time.perf_counter()
+    cpu_step(probe)
+    t_img = time.perf_counter() - t0
+    total_steps = max(args.steps, 1) + max(args.warmup, 1)
+    n_img = int(max(1, min(REF_SAMPLE_IMAGES, 180.0 / (total_steps * t_img))))
+    base = cpu_baseline(inp, full=False, steps=max(args.steps, 1), warmup=max(args.warmup, 1), n_images=n_img)
     return {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": W["name"], "classes": W["c"], "sigma_range": list(W["sigma_range"]),
-                   "sample_images_per_step": REF_SAMPLE_IMAGES},
+                   "sample_images_per_step": n_img},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -353,8 +373,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -233,6 +233,66 @@ size_t b200ssl_dice_workspace_bytes(int n, int64_t chw);
 int b200ssl_dice_from_cm(const long long* cm_per_image, int n_images, float* dice_out,
                          b200ssl_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The whole loss path of one semi-supervised step in one call (train.py:65-130 order): mask, fused
+ * mix of images + teacher predictions, Lovasz forward/backward (unit upstream gradient), EMA,
+ * confusion matrix of (labels, argmax scores).  Chains the entry points above on `stream`; any stage
+ * whose input pointer is NULL (noise / image_a / scores / ema_table / cm) is skipped.
+ *   mode BINARY : losses.binary_lovasz_loss_with_logits (losses.py:239-250); target = soft one-hot
+ *                 fp32 [n,C,h,w]; labels_u8 [n,h,w] and nonzero [n] are scratch/outputs
+ *   mode SOFTMAX: lovasz.lovasz_softmax with `lovasz` as given; target = integer labels [n,h,w]
+ * small: fp32[4] = {loss (out), denom (out, binary mode), upstream gradient (in, normally 1), pad}.
+ * --------------------------------------------------------------------------------------------- */
+#define B200SSL_STEP_BINARY 0
+#define B200SSL_STEP_SOFTMAX 1
+
+typedef struct b200ssl_step_desc {
+  int32_t n, classes, h, w, image_channels, K, mode, cm_has_ignore;
+  int64_t cm_ignore_index;
+  int32_t cm_label_dtype, reserved_;
+  b200ssl_lovasz_desc lovasz;
+  /* inputs */
+  const float* noise;      /* [n,1,h,w] */
+  const float* taps;       /* [n,K] */
+  const float* thr_factor; /* [n] */
+  const float* image_a;
+  const float* image_b;
+  const float* teacher_a;  /* may be NULL */
+  const float* teacher_b;
+  const float* scores;     /* [n,C,h,w] logits or probabilities */
+  const void* target;
+  const void* cm_labels;   /* NULL: the Lovasz labels */
+  /* outputs */
+  float* mask;
+  float* mixed_images;
+  float* mixed_teacher;
+  float* grad;             /* dLoss/dscores */
+  long long* cm;           /* [C,C], accumulated */
+  /* scratch (caller-owned) */
+  float* small;
+  float* jgrad;
+  float* seg_loss;
+  int32_t* seg_fg;
+  int32_t* seg_valid;
+  float* seg_scale;
+  int32_t* nonzero;
+  unsigned char* labels_u8;
+  void* ws_cowmix;
+  size_t ws_cowmix_bytes;
+  void* ws_lovasz;
+  size_t ws_lovasz_bytes;
+  /* EMA */
+  const b200ssl_ema_chunk* ema_table;
+  int64_t ema_entries;
+  double ema_alpha;
+} b200ssl_step_desc;
+
+int b200ssl_loss_path_step(const b200ssl_step_desc* d, b200ssl_stream_t stream);
+
+/* sizeof() of the ABI structs as compiled into the library, for binding self-checks:
+ * which = 0: b200ssl_ema_chunk, 1: b200ssl_lovasz_desc, 2: b200ssl_step_desc; else 0. */
+size_t b200ssl_sizeof(int which);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

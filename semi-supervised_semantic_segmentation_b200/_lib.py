@@ -37,6 +37,24 @@ class EmaChunk(C.Structure):
 
 _vp, _i, _i64, _sz, _d = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
 
+STEP_BINARY, STEP_SOFTMAX = 0, 1
+
+
+class StepDesc(C.Structure):
+    """b200ssl_step_desc (include/b200ssl.h)."""
+    _fields_ = (
+        [(k, C.c_int32) for k in ("n", "classes", "h", "w", "image_channels", "K", "mode", "cm_has_ignore")] +
+        [("cm_ignore_index", C.c_int64), ("cm_label_dtype", C.c_int32), ("reserved_", C.c_int32),
+         ("lovasz", LovaszDesc)] +
+        [(k, C.c_void_p) for k in ("noise", "taps", "thr_factor", "image_a", "image_b", "teacher_a", "teacher_b",
+                                   "scores", "target", "cm_labels", "mask", "mixed_images", "mixed_teacher",
+                                   "grad", "cm", "small", "jgrad", "seg_loss", "seg_fg", "seg_valid",
+                                   "seg_scale", "nonzero", "labels_u8")] +
+        [("ws_cowmix", C.c_void_p), ("ws_cowmix_bytes", C.c_size_t), ("ws_lovasz", C.c_void_p),
+         ("ws_lovasz_bytes", C.c_size_t), ("ema_table", C.c_void_p), ("ema_entries", C.c_int64),
+         ("ema_alpha", C.c_double)])
+
+
 # name -> (restype, argtypes); mirrors include/b200ssl.h one to one
 SIGNATURES = {
     "b200ssl_version": (_i, []),
@@ -63,6 +81,8 @@ SIGNATURES = {
     "b200ssl_dice_workspace_bytes": (_sz, [_i, _i64]),
     "b200ssl_dice_metric": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _sz, _vp]),
     "b200ssl_dice_from_cm": (_i, [_vp, _i, _vp, _vp]),
+    "b200ssl_loss_path_step": (_i, [C.POINTER(StepDesc), _vp]),
+    "b200ssl_sizeof": (_sz, [_i]),
 }
 
 
@@ -84,6 +104,10 @@ def _load():
 
 
 lib = _load()
+for _which, _struct in enumerate((EmaChunk, LovaszDesc, StepDesc)):
+    if lib.b200ssl_sizeof(_which) != C.sizeof(_struct):
+        raise ImportError(f"b200ssl: ctypes layout of {_struct.__name__} ({C.sizeof(_struct)} B) does not match "
+                          f"libb200ssl.so ({lib.b200ssl_sizeof(_which)} B); rebuild the library")
 
 
 def check(rc, what=""):

@@ -22,32 +22,81 @@ def kernel_size_for(sigma_max):
     return int(round(sigma_max * 3) * 2) + 1
 
 
+_x2_cache = {}
+
+
 def gaussian_taps(size, sigmas):
     """All per-sample tap vectors at once: [N, size] fp32 on the CPU.
 
     Batched restatement of cowmix.py:6-24.  For odd `size` the abscissa runs from -(k+1) to k-1
     (the reference's arange(-size//2, size//2)), i.e. the peak sits one tap right of centre.
-    Every elementwise op is the same ATen CPU op the reference issues per sample, so the values
-    are bit-identical to the reference's (tests/test_cowmix_host.py checks this).
+    Every elementwise op is the same ATen CPU op the reference issues per sample and the row sums
+    use the same inner reduction as its 1-D `gauss.sum()`, so the values are bit-identical to the
+    reference's (tests/test_host_logic.py checks this against the golden vectors).
     """
-    x = torch.arange(-size // 2, size // 2).float()
-    if size % 2 == 0:
-        x = x + 0.5
+    x2 = _x2_cache.get(size)
+    if x2 is None:
+        x = torch.arange(-size // 2, size // 2).float()
+        if size % 2 == 0:
+            x = x + 0.5
+        x2 = _x2_cache[size] = (-x.pow(2.0)).unsqueeze(0)
     denom = 2 * sigmas.float() ** 2                      # float(2 * sigma ** 2) per sample
-    g = torch.exp(-x.pow(2.0).unsqueeze(0) / denom.unsqueeze(1))
-    norm = torch.stack([row.sum() for row in g])        # 1-D sums, the reference's reduction order
-    return (g / norm.unsqueeze(1)).contiguous()
+    g = torch.exp(x2 / denom.unsqueeze(1))
+    return g / g.sum(1, keepdim=True)
 
 
 def draw_mask_parameters(n, mask_proportion_range, sigma_range):
-    """cowmix.py:44-51: p ~ U(lo,hi), sigma ~ logU(lo,hi), both from the CPU generator, p first."""
-    p_distribution = torch.distributions.Uniform(torch.tensor(mask_proportion_range[0]),
-                                                 torch.tensor(mask_proportion_range[1]))
-    p = p_distribution.rsample(sample_shape=[n])
-    log_lo, log_hi = math.log(float(sigma_range[0])), math.log(float(sigma_range[1]))
-    sigma_distribution = torch.distributions.Uniform(torch.tensor(log_lo), torch.tensor(log_hi))
-    sigmas = torch.exp(sigma_distribution.rsample([n]))
+    """cowmix.py:44-51: p ~ U(lo,hi), sigma ~ logU(lo,hi), both from the CPU generator, p first.
+    `Uniform(lo, hi).rsample([n])` is `lo + torch.rand([n]) * (hi - lo)` on fp32 scalars; issuing
+    those ops directly skips the distribution objects' argument validation (same bits, same RNG use)."""
+    lo, hi = torch.tensor(mask_proportion_range[0]), torch.tensor(mask_proportion_range[1])
+    p = lo + torch.rand([n], dtype=lo.dtype) * (hi - lo)
+    l0 = torch.tensor(math.log(float(sigma_range[0])))
+    l1 = torch.tensor(math.log(float(sigma_range[1])))
+    sigmas = torch.exp(l0 + torch.rand([n], dtype=l0.dtype) * (l1 - l0))
     return p, sigmas
+
+
+class _Staging:
+    """Ring of pinned host buffers for the per-step taps/factors upload; a slot is reused only after
+    the copy that read it has completed (event per slot), so the host can run ahead of the GPU."""
+
+    def __init__(self, slots=8):
+        self.slots = [None] * slots
+        self.events = [None] * slots
+        self.i = 0
+
+    def upload(self, taps, factors, device):
+        n_t, n_f = taps.numel(), factors.numel()
+        i = self.i
+        self.i = (i + 1) % len(self.slots)
+        buf = self.slots[i]
+        if buf is None or buf.numel() < n_t + n_f:
+            buf = self.slots[i] = torch.empty(max(n_t + n_f, 64 * 200), dtype=torch.float32, pin_memory=True)
+            self.events[i] = torch.cuda.Event()
+        else:
+            self.events[i].synchronize()
+        buf[:n_t].copy_(taps.reshape(-1))
+        buf[n_t:n_t + n_f].copy_(factors.reshape(-1))
+        dev = buf[:n_t + n_f].to(device, non_blocking=True)
+        self.events[i].record(torch.cuda.current_stream(device))
+        return dev
+
+
+_staging = {}
+
+
+def upload_mask_parameters(p, sigmas, device):
+    """Host part of cowmix.py:27-31 and :64: kernel size, taps and erfinv threshold factors, uploaded
+    in one pinned non-blocking copy.  Returns (size, device buffer [N*size taps | N factors])."""
+    size = kernel_size_for(sigmas.max().item())
+    taps = gaussian_taps(size, sigmas)
+    factors = (torch.erfinv(2 * p - 1) * math.sqrt(2.0)).float()          # cowmix.py:64
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _staging.get(key)
+    if st is None:
+        st = _staging[key] = _Staging()
+    return size, st.upload(taps, factors, device)
 
 
 def masks_from_noise(noise, p, sigmas, return_field=False):
@@ -66,13 +115,7 @@ def masks_from_noise(noise, p, sigmas, return_field=False):
     field = torch.empty_like(noise) if return_field else None
     if n == 0 or h == 0 or w == 0:
         return (mask, field) if return_field else mask
-    size = kernel_size_for(sigmas.max().item())
-    taps = gaussian_taps(size, sigmas)
-    factors = (torch.erfinv(2 * p - 1) * math.sqrt(2.0)).float()          # cowmix.py:64
-    host = torch.empty(n * size + n, dtype=torch.float32, pin_memory=True)
-    host[: n * size] = taps.reshape(-1)
-    host[n * size:] = factors.reshape(-1)
-    dev = host.to(noise.device, non_blocking=True)
+    size, dev = upload_mask_parameters(p, sigmas, noise.device)
     ws_bytes = lib.b200ssl_cowmix_workspace_bytes(n, h, w)
     ws = _lib.workspaces.get(noise.device, "cowmix", ws_bytes)
     with torch.cuda.device(noise.device):

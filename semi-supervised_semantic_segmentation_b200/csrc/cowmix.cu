@@ -14,12 +14,180 @@
 //   * Accumulation order is fixed: taps ascending, one fma per tap, starting from +0 -- the
 //     C oracle (oracle/oracle.c) does exactly the same and matches bit for bit.
 //   * Statistics are accumulated in fp64 per thread and reduced in a fixed order (deterministic).
+//
+// Fast path (conv_tma_tile_kernel): the input tile of a 64x64 output block -- (64 + K - 1) rows of
+// 64 columns -- is brought into shared memory by TMA (cp.async.bulk.tensor, 32-row boxes, one
+// mbarrier per box so the first rows can be consumed while the rest is in flight).  TMA zero-fills
+// rows/columns outside the image, which IS the convolution's zero padding, so the inner loop has
+// no bounds checks at all: per input row one 8-byte shared load of the data pair, one broadcast
+// 8-byte load of the duplicated tap, 16 FFMA2.  The four warps of a block share the tile (read
+// amplification (64+K-1)/64 instead of (16+K-1)/16 from L2).  Needs a 16-byte aligned base and a
+// fast-axis extent that is a multiple of 4 (tensor-map stride rule); other shapes take the generic
+// kernel below, which produces bit-identical results.
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 
 namespace b200ssl {
 
 constexpr int kConvR = 16;         // slow-axis outputs per thread
 constexpr int kConvThreads = 128;  // each thread covers 2 fast-axis positions
+
+// ---- TMA tile geometry ----
+constexpr int kTileCols = 64;                       // fast-axis columns per block (32 lanes x 2)
+constexpr int kTileWarps = 4;
+constexpr int kTileRowsOut = kTileWarps * kConvR;   // 64 output rows per block
+constexpr int kBoxRows = 32;                        // rows per TMA box / mbarrier
+constexpr int kMaxBoxes = 8;                        // 256 staged rows: enough for K <= 193
+constexpr int kBoxBytes = kBoxRows * kTileCols * 4; // 8 KiB
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2),
+      "r"(smem_u32(bar)) : "memory");
+}
+
+// in  : [n][A][B] through the tensor map (dims {B, A, n}, box {64, 32, 1})
+// out : [n][B][A];  out[n][b][a] = sum_{i<K} taps[n][i] * in[n][a + i - K/2][b]
+template <bool STATS>
+__global__ void __launch_bounds__(kTileWarps * 32, 3)
+conv_tma_tile_kernel(const __grid_constant__ CUtensorMap in_map, float* __restrict__ out,
+                     const float* __restrict__ taps, int K, int A, int B,
+                     double* __restrict__ partials) {
+  constexpr int R = kConvR;
+  extern __shared__ __align__(128) unsigned char conv_smem[];
+  float* tile = reinterpret_cast<float*>(conv_smem);                                   // [boxes*32][64]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(conv_smem + kMaxBoxes * kBoxBytes);
+  float2* wdup = reinterpret_cast<float2*>(conv_smem + kMaxBoxes * kBoxBytes + 64);     // [K + 3R]
+
+  const int n = blockIdx.z;
+  const int k = K >> 1;
+  const int a_blk = blockIdx.y * kTileRowsOut;
+  const int b_blk = blockIdx.x * kTileCols;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // steps per warp: t = 0 .. R+K-2 reads staged row 16*warp + t; padded to whole groups of R
+  const int groups = (R + K - 1 + R - 1) / R;
+  const int rows_staged = (kTileWarps - 1) * R + groups * R;
+  const int n_boxes = (rows_staged + kBoxRows - 1) / kBoxRows;  // <= kMaxBoxes (checked on the host)
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_boxes; ++i) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_boxes; ++i) {
+      mbar_expect_tx(&bars[i], kBoxBytes);
+      tma_load_3d(tile + i * kBoxRows * kTileCols, &in_map, b_blk, a_blk - k + i * kBoxRows, n, &bars[i]);
+    }
+  }
+  const int wlen = K + 3 * R;
+  for (int i = threadIdx.x; i < wlen; i += kTileWarps * 32) {
+    const int t = i - R;
+    const float w = (t >= 0 && t < K) ? __ldg(taps + (long long)n * K + t) : 0.f;
+    wdup[i] = make_float2(w, w);
+  }
+  __syncthreads();
+
+  float2 acc[R], wreg[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int s = 0; s < R; ++s) wreg[s] = wdup[s];  // taps t - R (all zero): slots of "previous" group
+  const float2* __restrict__ col = reinterpret_cast<const float2*>(tile) + lane;  // row pitch 32 float2
+
+  for (int g = 0; g < groups; ++g) {
+    const int row0 = (warp + g) * R;  // staged row of step s = 0 in this group
+    if (g == 0 || (row0 & (kBoxRows - 1)) == 0) mbar_wait(&bars[row0 / kBoxRows], 0);  // first box / entering a new box
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+      wreg[s] = wdup[g * R + s + R];
+      const float2 v = col[(row0 + s) * (kTileCols / 2)];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = __ffma2_rn(v, wreg[(s - r + R) % R], acc[r]);
+    }
+  }
+
+  // transposed store: for a fixed column the R outputs of this thread are contiguous in `out`
+  const int a0 = a_blk + warp * R;
+  float* __restrict__ oplane = out + (long long)n * A * B;
+  double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int b = b_blk + 2 * lane + half;
+    if (b < B && a0 < A) {
+      float* dst = oplane + (long long)b * A + a0;
+      float vals[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) vals[r] = half ? acc[r].y : acc[r].x;
+      if (a0 + R <= A && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+#pragma unroll
+        for (int q = 0; q < R / 4; ++q)
+          *reinterpret_cast<float4*>(dst + 4 * q) =
+              make_float4(vals[4 * q], vals[4 * q + 1], vals[4 * q + 2], vals[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (a0 + r < A) dst[r] = vals[r];
+      }
+      if (STATS) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (a0 + r < A) {
+            const double x = (double)vals[r];
+            s1 += x;
+            s2 += x * x;
+          }
+        }
+      }
+    }
+  }
+  if (STATS) {
+    __shared__ double red[2][kTileWarps];
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      red[0][warp] = s1;
+      red[1][warp] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+      for (int w = 0; w < kTileWarps; ++w) {
+        t1 += red[0][w];
+        t2 += red[1][w];
+      }
+      const long long blk = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+      const long long per_sample = (long long)gridDim.x * gridDim.y;
+      partials[(n * per_sample + blk) * 2 + 0] = t1;
+      partials[(n * per_sample + blk) * 2 + 1] = t2;
+    }
+  }
+}
 
 template <bool VEC2>
 __device__ __forceinline__ float2 load_pair(const float* __restrict__ row, int col, int B) {
@@ -204,11 +372,74 @@ cowmix_threshold_kernel(const float* __restrict__ S, const float* __restrict__ t
   }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// the TMA path needs: 16-byte aligned base, row pitch a multiple of 16 bytes, at least one full
+// column tile, and K small enough for the staged rows to fit the 8 boxes
+static bool conv_tma_ok(const float* in, int K, int A, int B) {
+  const int groups = (kConvR + K - 1 + kConvR - 1) / kConvR;
+  const int rows = (kTileWarps - 1) * kConvR + groups * kConvR;
+  return aligned16(in) && (B % 4 == 0) && B >= kTileCols && A >= 1 && rows <= kMaxBoxes * kBoxRows &&
+         tensor_map_encoder() != nullptr;
+}
+
 struct ConvGrid {
   dim3 grid;
   int partials_per_sample;
 };
-static ConvGrid conv_grid(int n, int A, int B) {
+static ConvGrid conv_tma_grid(int n, int A, int B) {
+  ConvGrid g;
+  g.grid = dim3((unsigned)((B + kTileCols - 1) / kTileCols), (unsigned)((A + kTileRowsOut - 1) / kTileRowsOut),
+                (unsigned)n);
+  g.partials_per_sample = (int)(g.grid.x * g.grid.y);
+  return g;
+}
+
+template <bool STATS>
+static int launch_conv_tma(const float* in, float* out, const float* taps, int K, int n, int A, int B,
+                           double* partials, cudaStream_t s, const char* name) {
+  CUtensorMap map;
+  const cuuint64_t dims[3] = {(cuuint64_t)B, (cuuint64_t)A, (cuuint64_t)n};
+  const cuuint64_t strides[2] = {(cuuint64_t)B * 4, (cuuint64_t)A * B * 4};
+  const cuuint32_t box[3] = {kTileCols, kBoxRows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = tensor_map_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(in), dims,
+                                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("%s: cuTensorMapEncodeTiled failed (%d)", name, (int)r);
+    return B200SSL_EUNSUPPORTED;
+  }
+  const size_t smem = (size_t)kMaxBoxes * kBoxBytes + 64 + (size_t)(K + 3 * kConvR) * sizeof(float2);
+  auto kern = conv_tma_tile_kernel<STATS>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxBoxes * kBoxBytes + 64 + (193 + 3 * kConvR) * sizeof(float2)));
+    attr_done = true;
+  }
+  const ConvGrid g = conv_tma_grid(n, A, B);
+  prof_begin(name, s);
+  kern<<<g.grid, kTileWarps * 32, smem, s>>>(map, out, taps, K, A, B, partials);
+  return check_launch(name);
+}
+
+static ConvGrid conv_grid(int n, int A, int B) {  // generic kernel
   ConvGrid g;
   g.grid = dim3((unsigned)((B + 2 * kConvThreads - 1) / (2 * kConvThreads)),
                 (unsigned)((A + kConvR - 1) / kConvR), (unsigned)n);
@@ -224,11 +455,11 @@ size_t b200ssl_cowmix_workspace_bytes(int n, int h, int w) {
   using namespace b200ssl;
   if (n <= 0 || h <= 0 || w <= 0) return 0;
   const size_t plane = (size_t)h * w;
-  const ConvGrid g2 = conv_grid(n, w, h);
+  const int pps = max(conv_grid(n, w, h).partials_per_sample, conv_tma_grid(n, w, h).partials_per_sample);
   size_t bytes = 0;
   bytes += align_up((size_t)n * plane * sizeof(float), 256);  // Vt
   bytes += align_up((size_t)n * plane * sizeof(float), 256);  // S (when field_out is NULL)
-  bytes += align_up((size_t)n * g2.partials_per_sample * 2 * sizeof(double), 256);
+  bytes += align_up((size_t)n * pps * 2 * sizeof(double), 256);
   return bytes;
 }
 
@@ -257,9 +488,13 @@ int b200ssl_cowmix_mask(const float* noise, const float* taps, int K, const floa
   cudaStream_t s = (cudaStream_t)stream;
   const size_t smem = (size_t)(K + 3 * kConvR) * sizeof(float2);
   B200SSL_REQUIRE(smem <= 48 * 1024, "cowmix_mask: K=%d too large", K);
+  B200SSL_REQUIRE(n <= 65535, "cowmix_mask: too many samples");
 
   // pass 1: along H (slow axis of noise[n][H][W]) -> Vt[n][W][H]
-  {
+  if (conv_tma_ok(noise, K, h, w)) {
+    int rc = launch_conv_tma<false>(noise, Vt, taps, K, n, h, w, nullptr, s, "cowmix_conv_pass1");
+    if (rc) return rc;
+  } else {
     const ConvGrid g = conv_grid(n, h, w);
     const bool vec2 = (w % 2 == 0) && ((reinterpret_cast<uintptr_t>(noise) & 7u) == 0);
     prof_begin("cowmix_conv_pass1", s);
@@ -271,8 +506,12 @@ int b200ssl_cowmix_mask(const float* noise, const float* taps, int K, const floa
     if (rc) return rc;
   }
   // pass 2: along W (slow axis of Vt[n][W][H]) -> S[n][H][W], with per-block statistics
-  const ConvGrid g2 = conv_grid(n, w, h);
-  {
+  const bool tma2 = conv_tma_ok(Vt, K, w, h);
+  const ConvGrid g2 = tma2 ? conv_tma_grid(n, w, h) : conv_grid(n, w, h);
+  if (tma2) {
+    int rc = launch_conv_tma<true>(Vt, S, taps, K, n, w, h, partials, s, "cowmix_conv_pass2");
+    if (rc) return rc;
+  } else {
     const bool vec2 = (h % 2 == 0);
     prof_begin("cowmix_conv_pass2", s);
     if (vec2)

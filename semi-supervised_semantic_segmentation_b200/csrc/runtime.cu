@@ -67,6 +67,15 @@ long long b200ssl_launch_count(void) {
   return b200ssl::g_launches.load(std::memory_order_relaxed);
 }
 
+size_t b200ssl_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(b200ssl_ema_chunk);
+    case 1: return sizeof(b200ssl_lovasz_desc);
+    case 2: return sizeof(b200ssl_step_desc);
+    default: return 0;
+  }
+}
+
 void b200ssl_prof_enable(int on) { b200ssl::g_prof_on.store(on ? 1 : 0); }
 
 long long b200ssl_prof_report(char* buf, size_t capacity) {

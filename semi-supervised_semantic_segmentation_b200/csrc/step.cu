@@ -1,0 +1,74 @@
+// One C call for the whole loss path of a semi-supervised step (train.py:65-130 order):
+//   mask (cowmix.py:56-68) -> fused mix of images and teacher predictions (cowmix.py:72-73 x2)
+//   -> Lovasz forward + backward (lovasz.py / losses.py:239-250) -> EMA (mean_teacher.py:10-11)
+//   -> confusion matrix of (labels, argmax scores).
+// It only chains the per-stage entry points of this library on one stream; the point is host cost:
+// ~20 kernel launches issued back to back from C (~2.5 us each) instead of ~20 Python/ctypes round
+// trips, so a 16x512x512 step stays GPU-bound.
+#include "common.cuh"
+
+extern "C" int b200ssl_loss_path_step(const b200ssl_step_desc* d, b200ssl_stream_t stream) {
+  using namespace b200ssl;
+  B200SSL_REQUIRE(d != nullptr, "loss_path_step: null descriptor");
+  B200SSL_REQUIRE(d->n >= 1 && d->classes >= 1 && d->h >= 1 && d->w >= 1, "loss_path_step: bad extents");
+  B200SSL_REQUIRE(d->mode == B200SSL_STEP_BINARY || d->mode == B200SSL_STEP_SOFTMAX, "loss_path_step: bad mode");
+  const int64_t hw = (int64_t)d->h * d->w;
+  int rc;
+
+  // 1. mask
+  if (d->noise) {
+    rc = b200ssl_cowmix_mask(d->noise, d->taps, d->K, d->thr_factor, d->n, d->h, d->w, d->mask, nullptr,
+                             d->ws_cowmix, d->ws_cowmix_bytes, stream);
+    if (rc) return rc;
+  }
+  // 2. mix images (+ teacher predictions) with the same mask
+  if (d->image_a) {
+    rc = b200ssl_mix2(d->image_a, d->image_b, d->mixed_images, d->image_channels, d->teacher_a, d->teacher_b,
+                      d->mixed_teacher, d->teacher_a ? d->classes : 0, d->mask, 1, d->n, hw, stream);
+    if (rc) return rc;
+  }
+  // 3. Lovasz forward + backward with a unit upstream gradient
+  if (d->scores) {
+    b200ssl_lovasz_desc ld = d->lovasz;
+    const void* labels = d->target;
+    if (d->mode == B200SSL_STEP_BINARY) {
+      // losses.py:240: int_target = argmax(target, 1); :246 w_i = (tgt.sum() > 0)
+      B200SSL_REQUIRE(d->labels_u8 && d->nonzero, "loss_path_step: binary mode needs labels_u8 / nonzero scratch");
+      cudaMemsetAsync(d->nonzero, 0, (size_t)d->n * sizeof(int32_t), (cudaStream_t)stream);
+      rc = b200ssl_argmax_channels(static_cast<const float*>(d->target), d->n, d->classes, hw, d->labels_u8,
+                                   B200SSL_U8, d->nonzero, stream);
+      if (rc) return rc;
+      labels = d->labels_u8;
+      ld.n_images = d->n; ld.n_channels = d->classes; ld.hw = hw; ld.per_image = 1;
+      ld.class_mode = B200SSL_LOVASZ_LIST; ld.n_list = 1; ld.class_list[0] = 1;
+      ld.has_ignore = 1; ld.ignore_index = 255; ld.label_dtype = B200SSL_U8;
+    }
+    float* loss = d->small;        // [0] loss  [1] denom  [2] upstream gradient (1.0)
+    rc = b200ssl_lovasz_forward(&ld, d->scores, labels, loss, d->seg_loss, d->seg_fg, d->seg_valid, d->jgrad,
+                                d->ws_lovasz, d->ws_lovasz_bytes, stream);
+    if (rc) return rc;
+    if (d->mode == B200SSL_STEP_BINARY) {
+      rc = b200ssl_binary_lovasz_reduce(d->seg_loss, d->nonzero, d->n, loss, d->small + 1, stream);
+      if (rc) return rc;
+      rc = b200ssl_binary_lovasz_scale(d->small + 2, d->nonzero, d->small + 1, d->n, d->seg_scale, stream);
+    } else {
+      rc = b200ssl_lovasz_seg_scale(&ld, d->small + 2, d->seg_fg, d->seg_valid, d->seg_scale, stream);
+    }
+    if (rc) return rc;
+    rc = b200ssl_lovasz_backward(&ld, d->seg_scale, d->jgrad, d->grad, stream);
+    if (rc) return rc;
+    // 5. confusion matrix of (labels, argmax scores)
+    if (d->cm) {
+      rc = b200ssl_confusion_from_logits(d->scores, d->cm_labels ? d->cm_labels : labels, d->n, d->classes, hw,
+                                         d->cm_has_ignore, d->cm_ignore_index,
+                                         d->cm_labels ? d->cm_label_dtype : ld.label_dtype, 0, d->cm, nullptr, stream);
+      if (rc) return rc;
+    }
+  }
+  // 4. EMA over all parameters
+  if (d->ema_table && d->ema_entries > 0) {
+    rc = b200ssl_ema_multi(d->ema_table, d->ema_entries, d->ema_alpha, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}

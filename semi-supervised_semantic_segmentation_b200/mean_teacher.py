@@ -15,6 +15,7 @@ from . import _lib
 from ._lib import lib, check, stream_ptr
 
 _tables = {}
+_data_ptr = torch.Tensor.data_ptr
 
 
 def _dense_like(a, b):
@@ -46,33 +47,43 @@ class EmaUpdater:
         self._table = None
         self._entries = 0
         self._host = None  # keeps the pinned staging buffer alive until the copy has run
+        self._device = None
 
-    def __call__(self, ema_params, params, alpha):
+    def prepare(self, ema_params, params):
+        """Returns (device table pointer, entries) for the given tensor lists, rebuilding the chunk table
+        only when a data pointer changed.  The per-call check is two C-level `map(data_ptr)` sweeps
+        (~35 us for 186 tensors); the full dtype/device/stride validation runs when the key changes."""
         if len(ema_params) != len(params):
             # zip() in the reference silently truncates; identically-built models never differ
             n = min(len(ema_params), len(params))
             ema_params, params = ema_params[:n], params[:n]
         if not params:
-            return
-        device = params[0].device
-        for e, p in zip(ema_params, params):
-            if not (e.is_cuda and p.is_cuda):
-                raise RuntimeError("b200ssl.mean_teacher: parameters must live on a CUDA device "
-                                   "(no CPU fallback)")
-            if e.device != device or p.device != device:
-                raise RuntimeError("b200ssl.mean_teacher: all parameters must be on one device")
-            if e.dtype != torch.float32 or p.dtype != torch.float32:
-                raise TypeError("b200ssl.mean_teacher: only float32 parameters are supported")
-            if not _dense_like(e, p):
-                raise ValueError("b200ssl.mean_teacher: teacher/student parameters must be dense "
-                                 "with identical shapes and strides")
-        key = (device, tuple((e.data_ptr(), p.data_ptr(), p.numel()) for e, p in zip(ema_params, params)))
+            return None, 0
+        key = (tuple(map(_data_ptr, ema_params)), tuple(map(_data_ptr, params)))
         if key != self._key:
+            device = params[0].device
+            for e, p in zip(ema_params, params):
+                if not (e.is_cuda and p.is_cuda):
+                    raise RuntimeError("b200ssl.mean_teacher: parameters must live on a CUDA device "
+                                       "(no CPU fallback)")
+                if e.device != device or p.device != device:
+                    raise RuntimeError("b200ssl.mean_teacher: all parameters must be on one device")
+                if e.dtype != torch.float32 or p.dtype != torch.float32:
+                    raise TypeError("b200ssl.mean_teacher: only float32 parameters are supported")
+                if not _dense_like(e, p):
+                    raise ValueError("b200ssl.mean_teacher: teacher/student parameters must be dense "
+                                     "with identical shapes and strides")
             self._table, self._entries, self._host = _build_table(ema_params, params, device)
             self._key = key
-        with torch.cuda.device(device):
-            check(lib.b200ssl_ema_multi(self._table.data_ptr(), self._entries, float(alpha),
-                                        stream_ptr(device)), "ema_multi")
+            self._device = device
+        return self._table.data_ptr(), self._entries
+
+    def __call__(self, ema_params, params, alpha):
+        table, entries = self.prepare(ema_params, params)
+        if not entries:
+            return
+        with torch.cuda.device(self._device):
+            check(lib.b200ssl_ema_multi(table, entries, float(alpha), stream_ptr(self._device)), "ema_multi")
 
 
 _default_updaters = {}
@@ -82,17 +93,24 @@ def update_ema_variables(model, ema_model, alpha):
     with torch.no_grad():
         # Use the true average until the exponential average is more correct
         # alpha = min(1 - 1 / (global_step + 1), alpha)
-        ema_params = [p.data for p in ema_model.parameters()]
-        params = [p.data for p in model.parameters()]
         key = (id(model), id(ema_model))
-        upd = _default_updaters.get(key)
-        if upd is None:
-            upd = _default_updaters[key] = EmaUpdater()
-        upd(ema_params, params, alpha)
+        ent = _default_updaters.get(key)
+        if ent is None or ent[3]() is not model or ent[4]() is not ema_model:
+            # walking the module tree costs ~0.5 ms for a few hundred parameters: do it once per model
+            # pair; the Parameter objects are stable, and a re-pointed `.data` changes data_ptr(), which
+            # EmaUpdater.prepare notices.  Call reset_cache() after adding or removing parameters.
+            import weakref
+            ent = _default_updaters[key] = (EmaUpdater(), list(ema_model.parameters()), list(model.parameters()),
+                                           weakref.ref(model), weakref.ref(ema_model))
+        ent[0](ent[1], ent[2], alpha)
 
         # mean_teacher.py:13-18: both branches re-point the teacher's buffer at the student's storage
         for ema_buffer, buffer in zip(ema_model.buffers(), model.buffers()):
             ema_buffer.data = buffer.data
+
+
+def reset_cache():
+    _default_updaters.clear()
 
 
 def detach_model_parameters(model):

@@ -6,15 +6,19 @@ Order (train.py:65-130):
     loss, dloss/dlogits = Lovasz (binary shim losses.py:239-250, or lovasz_softmax)          :51,:61
     update_ema_variables(model, ema_model, alpha)                                             :130
     confusion matrix of (labels, argmax logits)                                               (new)
-Nothing in here synchronises with the host; results are device tensors.
+
+Host work per step is what the reference also does on the host (2N uniform draws, N*K taps, N erfinv
+factors) plus ONE call into the C library (b200ssl_loss_path_step), which issues every kernel of the
+path back to back on the current stream.  Nothing in here synchronises with the host; results are
+device tensors.
 """
 import ctypes as C
 
 import torch
 
 from . import _lib
-from ._lib import lib, check, stream_ptr
-from . import cowmix, lovasz, losses, mean_teacher, metrics
+from ._lib import lib, check, require_cuda
+from . import cowmix, lovasz, mean_teacher
 
 
 class LossPathStep:
@@ -31,45 +35,43 @@ class LossPathStep:
         self.per_image = per_image
         self.ignore = ignore
         self._ema = mean_teacher.EmaUpdater()
+        self._scratch_key = None
+        self._scratch = None
+        self._small_init = None
 
-    # -- Lovasz loss and its gradient w.r.t. the logits/probabilities, without autograd bookkeeping
-    def lovasz_loss_and_grad(self, scores, target):
+    # scratch that never leaves this object is kept across steps (stream-ordered reuse)
+    def _get_scratch(self, scores, desc_l, n_seg):
         dev = scores.device
-        scores = scores.contiguous()
+        key = (dev, tuple(scores.shape), n_seg)
+        if key != self._scratch_key:
+            n, c, h, w = scores.shape
+            ws_c = lib.b200ssl_cowmix_workspace_bytes(n, h, w)
+            ws_l = lib.b200ssl_lovasz_workspace_bytes(C.byref(desc_l))
+            self._scratch = {
+                "jgrad": torch.empty_like(scores),
+                "segf": torch.empty(2 * max(n_seg, 1), dtype=torch.float32, device=dev),      # seg_loss | seg_scale
+                "segi": torch.empty(2 * max(n_seg, 1) + n, dtype=torch.int32, device=dev),    # seg_fg | seg_valid | nonzero
+                "ws_c": torch.empty(max(ws_c, 256), dtype=torch.uint8, device=dev),
+                "ws_l": torch.empty(max(ws_l, 256), dtype=torch.uint8, device=dev),
+            }
+            self._small_init = torch.tensor([0.0, 0.0, 1.0, 0.0], dtype=torch.float32, device=dev)
+            self._scratch_key = key
+        return self._scratch
+
+    def _lovasz_desc(self, scores, target):
         if self.mode == "binary":
-            labels, nonzero = losses.argmax_channels(target)
-            desc = lovasz._make_desc(scores, labels, [1], True, 255)
-        else:
-            labels = target.contiguous()
-            desc = lovasz._make_desc(scores, labels, self.classes, self.per_image, self.ignore)
-        n_seg = lib.b200ssl_lovasz_num_segments(C.byref(desc))
-        if n_seg < 0:
-            check(n_seg, "lovasz_num_segments")
-        small = torch.empty(4 + 2 * n_seg, dtype=torch.float32, device=dev)   # loss, denom, one, pad, seg_loss, seg_scale
-        seg_meta = torch.empty((2, max(n_seg, 1)), dtype=torch.int32, device=dev)
-        jgrad = torch.empty_like(scores)
-        grad = torch.empty_like(scores)
-        ws = _lib.workspaces.get(dev, "lovasz", lib.b200ssl_lovasz_workspace_bytes(C.byref(desc)))
-        s = stream_ptr(dev)
-        base = small.data_ptr()
-        seg_loss_p, seg_scale_p = base + 16, base + 16 + 4 * n_seg
-        with torch.cuda.device(dev):
-            small[2] = 1.0  # upstream gradient of the scalar loss
-            check(lib.b200ssl_lovasz_forward(
-                C.byref(desc), scores.data_ptr(), labels.data_ptr(), base, seg_loss_p,
-                seg_meta[0].data_ptr(), seg_meta[1].data_ptr(), jgrad.data_ptr(), ws.data_ptr(),
-                ws.numel(), s), "lovasz_forward")
-            if self.mode == "binary":
-                check(lib.b200ssl_binary_lovasz_reduce(seg_loss_p, nonzero.data_ptr(), n_seg, base, base + 4, s),
-                      "binary_lovasz_reduce")
-                check(lib.b200ssl_binary_lovasz_scale(base + 8, nonzero.data_ptr(), base + 4, n_seg, seg_scale_p, s),
-                      "binary_lovasz_scale")
-            else:
-                check(lib.b200ssl_lovasz_seg_scale(C.byref(desc), base + 8, seg_meta[0].data_ptr(),
-                                                   seg_meta[1].data_ptr(), seg_scale_p, s), "lovasz_seg_scale")
-            check(lib.b200ssl_lovasz_backward(C.byref(desc), seg_scale_p, jgrad.data_ptr(), grad.data_ptr(), s),
-                  "lovasz_backward")
-        return small[0], grad, labels
+            d = _lib.LovaszDesc()
+            d.n_images, d.n_channels, d.hw = scores.shape[0], scores.shape[1], scores.shape[2] * scores.shape[3]
+            d.per_image, d.class_mode, d.n_list = 1, _lib.LOVASZ_LIST, 1
+            d.class_list[0] = 1
+            d.has_ignore, d.ignore_index, d.label_dtype = 1, 255, _lib.U8
+            return d
+        return lovasz._make_desc(scores, target, self.classes, self.per_image, self.ignore)
+
+    def lovasz_loss_and_grad(self, scores, target):
+        """Lovasz loss and its gradient w.r.t. the scores only (no mask / mix / EMA / matrix)."""
+        out = self._run(None, None, None, None, scores, target, None, None, None, None, want_cm=False)
+        return out["loss"], out["grad"], out["labels"]
 
     def __call__(self, image_a, image_b, teacher_a, teacher_b, scores, target, params, ema_params,
                  cm_labels=None, cm_out=None):
@@ -77,13 +79,88 @@ class LossPathStep:
         target: soft one-hot [N,C,H,W] (binary mode) or integer labels [N,H,W] (softmax mode);
         params / ema_params: lists of student / teacher parameter tensors;
         cm_labels: integer labels for the confusion matrix (defaults to the Lovasz labels)."""
+        return self._run(image_a, image_b, teacher_a, teacher_b, scores, target, params, ema_params,
+                         cm_labels, cm_out, want_cm=True)
+
+    def _run(self, image_a, image_b, teacher_a, teacher_b, scores, target, params, ema_params,
+             cm_labels, cm_out, want_cm):
         with torch.no_grad():
-            mask = cowmix.generate_cowmix_masks_like(image_a, self.mask_proportion_range, self.sigma_range)
-            mixed_images, mixed_teacher = cowmix.mix2_with_mask(image_a, image_b, teacher_a, teacher_b, mask)
-            loss, grad, labels = self.lovasz_loss_and_grad(scores, target)
-            self._ema(ema_params, params, self.ema_alpha)
-            cm = metrics.confusion_matrix_from_logits(
-                scores, labels if cm_labels is None else cm_labels,
-                ignore_index=self.ignore, out=cm_out)
-        return {"mask": mask, "mixed_images": mixed_images, "mixed_teacher": mixed_teacher,
-                "loss": loss, "grad": grad, "cm": cm}
+            require_cuda(scores, "scores", torch.float32)
+            dev = scores.device
+            scores = scores.contiguous()
+            target = target.contiguous()
+            n, c, h, w = scores.shape
+            binary = self.mode == "binary"
+            if binary:
+                require_cuda(target, "target", torch.float32)
+                if target.shape != scores.shape:
+                    raise ValueError("binary mode: target must be a soft one-hot tensor shaped like the scores")
+            else:
+                require_cuda(target, "target")
+            desc_l = self._lovasz_desc(scores, target)
+            n_seg = lib.b200ssl_lovasz_num_segments(C.byref(desc_l))
+            if n_seg < 0:
+                check(n_seg, "lovasz_num_segments")
+            sc = self._get_scratch(scores, desc_l, n_seg)
+            ns = max(n_seg, 1)
+
+            d = _lib.StepDesc()
+            d.n, d.classes, d.h, d.w = n, c, h, w
+            d.mode = _lib.STEP_BINARY if binary else _lib.STEP_SOFTMAX
+            d.lovasz = desc_l
+            out = {}
+            # ---- mask + mix (skipped when no images are given)
+            if image_a is not None:
+                require_cuda(image_a, "image_a", torch.float32)
+                p, sigmas = cowmix.draw_mask_parameters(n, self.mask_proportion_range, self.sigma_range)
+                size, taps_dev = cowmix.upload_mask_parameters(p, sigmas, dev)
+                noise = torch.normal(mean=0, std=1, size=(n, 1, h, w), dtype=torch.float32, device=dev)
+                image_a, image_b = image_a.contiguous(), image_b.contiguous()
+                mask = torch.empty_like(noise)
+                mixed_images = torch.empty_like(image_a)
+                d.K, d.image_channels = size, image_a.shape[1]
+                d.noise, d.taps, d.thr_factor = noise.data_ptr(), taps_dev.data_ptr(), taps_dev.data_ptr() + 4 * n * size
+                d.image_a, d.image_b = image_a.data_ptr(), image_b.data_ptr()
+                d.mask, d.mixed_images = mask.data_ptr(), mixed_images.data_ptr()
+                out["mask"], out["mixed_images"] = mask, mixed_images
+                if teacher_a is not None:
+                    teacher_a, teacher_b = teacher_a.contiguous(), teacher_b.contiguous()
+                    mixed_teacher = torch.empty_like(teacher_a)
+                    d.teacher_a, d.teacher_b, d.mixed_teacher = teacher_a.data_ptr(), teacher_b.data_ptr(), mixed_teacher.data_ptr()
+                    out["mixed_teacher"] = mixed_teacher
+                d.ws_cowmix, d.ws_cowmix_bytes = sc["ws_c"].data_ptr(), sc["ws_c"].numel()
+            # ---- Lovasz
+            small = self._small_init.clone()
+            grad = torch.empty_like(scores)
+            d.scores, d.target = scores.data_ptr(), target.data_ptr()
+            d.grad, d.small, d.jgrad = grad.data_ptr(), small.data_ptr(), sc["jgrad"].data_ptr()
+            d.seg_loss, d.seg_scale = sc["segf"].data_ptr(), sc["segf"].data_ptr() + 4 * ns
+            d.seg_fg, d.seg_valid = sc["segi"].data_ptr(), sc["segi"].data_ptr() + 4 * ns
+            d.nonzero = sc["segi"].data_ptr() + 8 * ns
+            d.ws_lovasz, d.ws_lovasz_bytes = sc["ws_l"].data_ptr(), sc["ws_l"].numel()
+            if binary:
+                labels = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
+                d.labels_u8 = labels.data_ptr()
+            else:
+                labels = target
+            # ---- confusion matrix
+            if want_cm:
+                if cm_out is None:
+                    cm_out = torch.zeros((c, c), dtype=torch.int64, device=dev)
+                d.cm = cm_out.data_ptr()
+                d.cm_has_ignore = 0 if self.ignore is None else 1
+                d.cm_ignore_index = 0 if self.ignore is None else int(self.ignore)
+                if cm_labels is not None:
+                    cm_labels = cm_labels.contiguous()
+                    d.cm_labels, d.cm_label_dtype = cm_labels.data_ptr(), _lib.label_dtype_code(cm_labels)
+                out["cm"] = cm_out
+            # ---- EMA
+            if params is not None:
+                table, entries = self._ema.prepare(ema_params, params)
+                if entries:
+                    d.ema_table, d.ema_entries, d.ema_alpha = table, entries, float(self.ema_alpha)
+            with torch.cuda.device(dev):
+                check(lib.b200ssl_loss_path_step(C.byref(d), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                      "loss_path_step")
+            out["loss"], out["grad"], out["labels"] = small[0], grad, labels
+            return out

@@ -43,6 +43,9 @@ def test_struct_layouts_match_the_header():
     # int32 x2, int64, int32 x3, int32[64], int32, (pad) int64, int32 x2
     assert C.sizeof(_lib.LovaszDesc) == 8 + 8 + 12 + 256 + 4 + 8 + 8
     assert _lib.LovaszDesc.ignore_index.offset % 8 == 0
+    for which, st in enumerate((_lib.EmaChunk, _lib.LovaszDesc, _lib.StepDesc)):
+        assert _lib.lib.b200ssl_sizeof(which) == C.sizeof(st)
+    assert _lib.lib.b200ssl_sizeof(99) == 0
 
 
 def test_argument_errors_without_gpu():

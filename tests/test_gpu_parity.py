@@ -487,3 +487,36 @@ def test_loss_path_step_matches_oracle(ssl, dev):
         assert np.array_equal(bits(a), bits(b.cpu().numpy()))
     o_cm, _ = oracle.confusion_matrix(lab.numpy(), logits.argmax(1).numpy(), c, ignore_index=255)
     assert np.array_equal(out["cm"].cpu().numpy(), o_cm)
+
+
+def test_loss_path_step_softmax_mode(ssl, dev):
+    """configs[2]-shaped (21 classes, probabilities, batch-level 'present') through the fused C entry."""
+    gen = torch.Generator().manual_seed(33)
+    n, c, h, w = 2, 21, 64, 80
+    ia, ib = torch.rand(n, 3, h, w, generator=gen), torch.rand(n, 3, h, w, generator=gen)
+    ta, tb = torch.randn(n, c, h, w, generator=gen), torch.randn(n, c, h, w, generator=gen)
+    probas = torch.softmax(torch.randn(n, c, h, w, generator=gen) * 2, 1)
+    lab = coherent_labels(gen, n, 7, h, w)
+    lab[torch.rand(n, h, w, generator=gen) < 0.05] = 255
+    params = [torch.randn(s, generator=gen) for s in [(33, 7), (9000,)]]
+    ema = [torch.randn(p.shape, generator=gen) for p in params]
+    d = lambda t: t.to(dev)
+    step = ssl.LossPathStep(num_classes=c, sigma_range=(2, 5), mode="softmax", classes="present",
+                            per_image=False, ignore=255)
+    d_ema = [d(t) for t in ema]
+    out = step(d(ia), d(ib), d(ta), d(tb), d(probas), d(lab), [d(t) for t in params], d_ema)
+    mask = out["mask"].cpu().numpy()
+    assert same_floats(out["mixed_images"].cpu().numpy(), oracle.mix(ia.numpy(), ib.numpy(), mask))
+    assert same_floats(out["mixed_teacher"].cpu().numpy(), oracle.mix(ta.numpy(), tb.numpy(), mask))
+    o_loss, o_grad, _ = oracle.lovasz_softmax(probas.numpy(), lab.numpy(), classes="present", ignore=255)
+    assert abs(float(out["loss"]) - float(o_loss)) <= REL * abs(float(o_loss))
+    assert same_nonzero_bits(out["grad"].cpu().numpy(), o_grad)
+    o_cm, _ = oracle.confusion_matrix(lab.numpy(), probas.argmax(1).numpy(), c, ignore_index=255)
+    assert np.array_equal(out["cm"].cpu().numpy(), o_cm)
+    e_np = [t.numpy().copy() for t in ema]
+    oracle.ema_update(e_np, [t.numpy() for t in params], 0.99)
+    for a, b in zip(e_np, d_ema):
+        assert np.array_equal(bits(a), bits(b.cpu().numpy()))
+    # Lovasz-only entry and a second step reuse the cached scratch
+    loss2, grad2, _ = step.lovasz_loss_and_grad(d(probas), d(lab))
+    assert float(loss2) == float(out["loss"]) and torch.equal(grad2, out["grad"])
