@@ -135,6 +135,7 @@ def algorithmic_bytes(P, C, n_params, label_bytes=1):
         "mix2": 4 * (3 * 3 + 3 * C + 1) * P,
         "argmax_channels": (4 * C + label_bytes) * P,
         "lovasz_keybuild": (4 + label_bytes + 8) * P,
+        "lovasz_binary_prep": (8 * C + label_bytes + 8) * P,
         "lovasz_sort_pass0": 16 * P, "lovasz_sort_pass1": 16 * P, "lovasz_sort_pass2": 16 * P,
         "lovasz_rank_grad_pass3": 12 * P,
         "lovasz_backward": 8 * elems,
@@ -215,33 +216,53 @@ def run_b200(args, rank, world, local_rank):
     _lib.kernel_times(False)
 
     # ---- end to end: pinned host inputs -> H2D -> step -> D2H of loss + confusion matrix ----
+    # Every step copies its own 234.9 MB of inputs from pinned host memory and reads its loss and
+    # confusion matrix back.  The copies run on a second stream into two alternating device buffer
+    # sets, so the upload of step i+1 overlaps the kernels of step i (the host still waits for each
+    # step's result before it issues the next step, as a training loop reading the loss would).
     names = ["image_a", "image_b", "teacher_a", "teacher_b", "scores", "target"]
     host = {k: inp[k].cpu().pin_memory() for k in names}
-    dev_in = {k: torch.empty_like(inp[k]) for k in names}
+    dev_in = [{k: torch.empty_like(inp[k]) for k in names} for _ in range(2)]
     h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in names)
-    res_host = torch.empty(1 + W["c"] * W["c"], dtype=torch.float64).pin_memory()
+    res_host = [torch.empty(1 + W["c"] * W["c"], dtype=torch.float64).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device)
+    main_stream = torch.cuda.current_stream(device)
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step():
-        for k in names:
-            dev_in[k].copy_(host[k], non_blocking=True)
-        o = step(dev_in["image_a"], dev_in["image_b"], dev_in["teacher_a"], dev_in["teacher_b"],
-                 dev_in["scores"], dev_in["target"], inp["params"], inp["ema_params"])
-        if world > 1:
-            cm, sc = reducer.all_reduce(o["cm"], [o["loss"]])
-            packed = torch.cat([sc.reshape(-1)[:1], cm.reshape(-1).to(torch.float64)])
-        else:
-            packed = torch.cat([o["loss"].reshape(1).to(torch.float64), o["cm"].reshape(-1).to(torch.float64)])
-        res_host.copy_(packed, non_blocking=True)
-        torch.cuda.current_stream(device).synchronize()     # the caller reads the loss every step
-        return res_host
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])       # the step that last read this buffer set is done
+            for k in names:
+                dev_in[slot][k].copy_(host[k], non_blocking=True)
+            copied[slot].record(copy_stream)
 
-    for _ in range(3):
-        e2e_step()
+    def e2e_run(k_steps):
+        for sl in range(2):
+            consumed[sl].record(main_stream)
+        upload(0)
+        for i in range(k_steps):
+            sl = i & 1
+            if i + 1 < k_steps:
+                upload(sl ^ 1)
+            main_stream.wait_event(copied[sl])
+            b = dev_in[sl]
+            o = step(b["image_a"], b["image_b"], b["teacher_a"], b["teacher_b"], b["scores"], b["target"],
+                     inp["params"], inp["ema_params"])
+            consumed[sl].record(main_stream)
+            if world > 1:
+                cm, scs = reducer.all_reduce(o["cm"], [o["loss"]])
+                packed = torch.cat([scs.reshape(-1)[:1], cm.reshape(-1).to(torch.float64)])
+            else:
+                packed = torch.cat([o["loss"].reshape(1).to(torch.float64), o["cm"].reshape(-1).to(torch.float64)])
+            res_host[sl].copy_(packed, non_blocking=True)
+            main_stream.synchronize()                    # the caller reads the loss every step
+
+    e2e_run(3)
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     e3.record()
     sync_all()
     ms_e2e = torch.tensor([e2.elapsed_time(e3)], device=device, dtype=torch.float64)
@@ -292,7 +313,7 @@ def run_b200(args, rank, world, local_rank):
                    "l2": "no flush: the 234 MB of step inputs (+268 MB outputs/workspace) exceed the 126 MB L2"},
         "clocks": clock_info,
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": res_host.numel() * 8, "ms_per_step": round(ms_e2e / args.steps, 4)},
+                "d2h_bytes_per_step": res_host[0].numel() * 8, "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": int(launches),
         "roofline": roof,
     }

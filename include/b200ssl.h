@@ -170,6 +170,19 @@ int b200ssl_lovasz_forward(const b200ssl_lovasz_desc* d, const float* probas, co
                            float* loss_out, float* seg_loss, int32_t* seg_fg, int32_t* seg_valid,
                            float* jgrad, void* workspace, size_t workspace_bytes,
                            b200ssl_stream_t stream);
+/* Forward and backward in one go when the upstream gradient of the scalar loss is already known
+ * (device scalar grad_out, normally 1): the last radix pass writes the FINAL gradient
+ *   grad_probas[n,c,i] = RN(scale_seg * delta) * sign      (the same values b200ssl_lovasz_backward
+ * produces from jgrad and b200ssl_lovasz_seg_scale / b200ssl_binary_lovasz_scale), so neither the
+ * unit-gradient buffer nor a separate backward launch is needed.
+ *   binary_nonzero == NULL : loss_out = lovasz_softmax's scalar, scale as b200ssl_lovasz_seg_scale
+ *   binary_nonzero != NULL : losses.binary_lovasz_loss_with_logits (needs per_image, one class):
+ *       loss_out = sum_i w_i L_i / denom, denom_out = sum_i w_i + 0.001, w_i = binary_nonzero[i] > 0 */
+int b200ssl_lovasz_forward_backward(const b200ssl_lovasz_desc* d, const float* probas, const void* labels,
+                                    const float* grad_out, const int32_t* binary_nonzero, float* loss_out,
+                                    float* denom_out, float* seg_loss, int32_t* seg_fg, int32_t* seg_valid,
+                                    float* grad_probas, void* workspace, size_t workspace_bytes,
+                                    b200ssl_stream_t stream);
 int b200ssl_lovasz_seg_scale(const b200ssl_lovasz_desc* d, const float* grad_out,
                              const int32_t* seg_fg, const int32_t* seg_valid, float* seg_scale,
                              b200ssl_stream_t stream);
@@ -188,6 +201,20 @@ int b200ssl_lovasz_backward(const b200ssl_lovasz_desc* d, const float* seg_scale
  * L_i (seg_loss of a per_image, single-class forward); *_scale produces the per-segment upstream
  * gradients RN(grad_out / denom) * w_i for b200ssl_lovasz_backward.
  * --------------------------------------------------------------------------------------------- */
+/* The whole of losses.binary_lovasz_loss_with_logits, forward and backward, with a fused front end:
+ * ONE pass over target and scores yields labels_out = argmax_c target (uint8 [n,hw]), nonzero[n],
+ * the sort words of class `cls` and -- if cm != NULL -- the confusion matrix cm[label*C + argmax_c
+ * scores] (accumulated, int64 [C,C]); then the radix passes write grad = dLoss/dscores for the
+ * upstream gradient *grad_out.  Replaces b200ssl_argmax_channels + b200ssl_lovasz_forward_backward +
+ * b200ssl_confusion_from_logits.  Returns B200SSL_EUNSUPPORTED (nothing launched) unless
+ * 2 <= n_channels <= 16, hw % 4 == 0 and the planes are 16-byte aligned; workspace as for a
+ * per_image, single-class b200ssl_lovasz_desc. */
+int b200ssl_binary_lovasz_fused(const float* scores, const float* target, int n_images, int n_channels,
+                                int64_t hw, int cls, const float* grad_out, unsigned char* labels_out,
+                                int32_t* nonzero, float* loss_out, float* denom_out, float* seg_loss,
+                                int32_t* seg_fg, int32_t* seg_valid, float* grad, long long* cm,
+                                int cm_has_ignore, int64_t cm_ignore_index, void* workspace,
+                                size_t workspace_bytes, b200ssl_stream_t stream);
 int b200ssl_argmax_channels(const float* x, int n_images, int n_channels, int64_t hw,
                             void* labels_out, int out_dtype, int32_t* nonzero_out,
                             b200ssl_stream_t stream);
@@ -270,11 +297,9 @@ typedef struct b200ssl_step_desc {
   long long* cm;           /* [C,C], accumulated */
   /* scratch (caller-owned) */
   float* small;
-  float* jgrad;
   float* seg_loss;
   int32_t* seg_fg;
   int32_t* seg_valid;
-  float* seg_scale;
   int32_t* nonzero;
   unsigned char* labels_u8;
   void* ws_cowmix;

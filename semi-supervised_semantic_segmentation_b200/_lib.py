@@ -48,8 +48,8 @@ class StepDesc(C.Structure):
          ("lovasz", LovaszDesc)] +
         [(k, C.c_void_p) for k in ("noise", "taps", "thr_factor", "image_a", "image_b", "teacher_a", "teacher_b",
                                    "scores", "target", "cm_labels", "mask", "mixed_images", "mixed_teacher",
-                                   "grad", "cm", "small", "jgrad", "seg_loss", "seg_fg", "seg_valid",
-                                   "seg_scale", "nonzero", "labels_u8")] +
+                                   "grad", "cm", "small", "seg_loss", "seg_fg", "seg_valid",
+                                   "nonzero", "labels_u8")] +
         [("ws_cowmix", C.c_void_p), ("ws_cowmix_bytes", C.c_size_t), ("ws_lovasz", C.c_void_p),
          ("ws_lovasz_bytes", C.c_size_t), ("ema_table", C.c_void_p), ("ema_entries", C.c_int64),
          ("ema_alpha", C.c_double)])
@@ -71,8 +71,10 @@ SIGNATURES = {
     "b200ssl_lovasz_num_segments": (C.c_int32, [C.POINTER(LovaszDesc)]),
     "b200ssl_lovasz_workspace_bytes": (_sz, [C.POINTER(LovaszDesc)]),
     "b200ssl_lovasz_forward": (_i, [C.POINTER(LovaszDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200ssl_lovasz_forward_backward": (_i, [C.POINTER(LovaszDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200ssl_lovasz_seg_scale": (_i, [C.POINTER(LovaszDesc), _vp, _vp, _vp, _vp, _vp]),
     "b200ssl_lovasz_backward": (_i, [C.POINTER(LovaszDesc), _vp, _vp, _vp, _vp]),
+    "b200ssl_binary_lovasz_fused": (_i, [_vp, _vp, _i, _i, _i64, _i] + [_vp] * 10 + [_i, _i64, _vp, _sz, _vp]),
     "b200ssl_argmax_channels": (_i, [_vp, _i, _i, _i64, _vp, _i, _vp, _vp]),
     "b200ssl_binary_lovasz_reduce": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "b200ssl_binary_lovasz_scale": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),

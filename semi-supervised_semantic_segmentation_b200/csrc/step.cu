@@ -27,42 +27,55 @@ extern "C" int b200ssl_loss_path_step(const b200ssl_step_desc* d, b200ssl_stream
                       d->mixed_teacher, d->teacher_a ? d->classes : 0, d->mask, 1, d->n, hw, stream);
     if (rc) return rc;
   }
-  // 3. Lovasz forward + backward with a unit upstream gradient
+  // 3. Lovasz forward + backward with the upstream gradient small[2], 5. confusion matrix
   if (d->scores) {
-    b200ssl_lovasz_desc ld = d->lovasz;
-    const void* labels = d->target;
+    float* loss = d->small;        // [0] loss  [1] denom  [2] upstream gradient (1.0)
+    bool done = false;
     if (d->mode == B200SSL_STEP_BINARY) {
       // losses.py:240: int_target = argmax(target, 1); :246 w_i = (tgt.sum() > 0)
       B200SSL_REQUIRE(d->labels_u8 && d->nonzero, "loss_path_step: binary mode needs labels_u8 / nonzero scratch");
-      cudaMemsetAsync(d->nonzero, 0, (size_t)d->n * sizeof(int32_t), (cudaStream_t)stream);
-      rc = b200ssl_argmax_channels(static_cast<const float*>(d->target), d->n, d->classes, hw, d->labels_u8,
-                                   B200SSL_U8, d->nonzero, stream);
-      if (rc) return rc;
-      labels = d->labels_u8;
-      ld.n_images = d->n; ld.n_channels = d->classes; ld.hw = hw; ld.per_image = 1;
-      ld.class_mode = B200SSL_LOVASZ_LIST; ld.n_list = 1; ld.class_list[0] = 1;
-      ld.has_ignore = 1; ld.ignore_index = 255; ld.label_dtype = B200SSL_U8;
+      // fused front end: labels, weights, sort words and (when it uses the same labels) the matrix in one pass
+      rc = b200ssl_binary_lovasz_fused(d->scores, static_cast<const float*>(d->target), d->n, d->classes, hw, 1,
+                                       d->small + 2, d->labels_u8, d->nonzero, loss, d->small + 1, d->seg_loss,
+                                       d->seg_fg, d->seg_valid, d->grad, d->cm_labels ? nullptr : d->cm,
+                                       d->cm_has_ignore, d->cm_ignore_index, d->ws_lovasz, d->ws_lovasz_bytes,
+                                       stream);
+      if (rc == 0) {
+        done = true;
+        if (d->cm && d->cm_labels) {
+          rc = b200ssl_confusion_from_logits(d->scores, d->cm_labels, d->n, d->classes, hw, d->cm_has_ignore,
+                                             d->cm_ignore_index, d->cm_label_dtype, 0, d->cm, nullptr, stream);
+          if (rc) return rc;
+        }
+      } else if (rc != B200SSL_EUNSUPPORTED) {
+        return rc;
+      }
     }
-    float* loss = d->small;        // [0] loss  [1] denom  [2] upstream gradient (1.0)
-    rc = b200ssl_lovasz_forward(&ld, d->scores, labels, loss, d->seg_loss, d->seg_fg, d->seg_valid, d->jgrad,
-                                d->ws_lovasz, d->ws_lovasz_bytes, stream);
-    if (rc) return rc;
-    if (d->mode == B200SSL_STEP_BINARY) {
-      rc = b200ssl_binary_lovasz_reduce(d->seg_loss, d->nonzero, d->n, loss, d->small + 1, stream);
+    if (!done) {
+      b200ssl_lovasz_desc ld = d->lovasz;
+      const void* labels = d->target;
+      if (d->mode == B200SSL_STEP_BINARY) {
+        cudaMemsetAsync(d->nonzero, 0, (size_t)d->n * sizeof(int32_t), (cudaStream_t)stream);
+        rc = b200ssl_argmax_channels(static_cast<const float*>(d->target), d->n, d->classes, hw, d->labels_u8,
+                                     B200SSL_U8, d->nonzero, stream);
+        if (rc) return rc;
+        labels = d->labels_u8;
+        ld.n_images = d->n; ld.n_channels = d->classes; ld.hw = hw; ld.per_image = 1;
+        ld.class_mode = B200SSL_LOVASZ_LIST; ld.n_list = 1; ld.class_list[0] = 1;
+        ld.has_ignore = 1; ld.ignore_index = 255; ld.label_dtype = B200SSL_U8;
+      }
+      rc = b200ssl_lovasz_forward_backward(&ld, d->scores, labels, d->small + 2,
+                                           d->mode == B200SSL_STEP_BINARY ? d->nonzero : nullptr, loss,
+                                           d->small + 1, d->seg_loss, d->seg_fg, d->seg_valid, d->grad,
+                                           d->ws_lovasz, d->ws_lovasz_bytes, stream);
       if (rc) return rc;
-      rc = b200ssl_binary_lovasz_scale(d->small + 2, d->nonzero, d->small + 1, d->n, d->seg_scale, stream);
-    } else {
-      rc = b200ssl_lovasz_seg_scale(&ld, d->small + 2, d->seg_fg, d->seg_valid, d->seg_scale, stream);
-    }
-    if (rc) return rc;
-    rc = b200ssl_lovasz_backward(&ld, d->seg_scale, d->jgrad, d->grad, stream);
-    if (rc) return rc;
-    // 5. confusion matrix of (labels, argmax scores)
-    if (d->cm) {
-      rc = b200ssl_confusion_from_logits(d->scores, d->cm_labels ? d->cm_labels : labels, d->n, d->classes, hw,
-                                         d->cm_has_ignore, d->cm_ignore_index,
-                                         d->cm_labels ? d->cm_label_dtype : ld.label_dtype, 0, d->cm, nullptr, stream);
-      if (rc) return rc;
+      if (d->cm) {
+        rc = b200ssl_confusion_from_logits(d->scores, d->cm_labels ? d->cm_labels : labels, d->n, d->classes, hw,
+                                           d->cm_has_ignore, d->cm_ignore_index,
+                                           d->cm_labels ? d->cm_label_dtype : ld.label_dtype, 0, d->cm, nullptr,
+                                           stream);
+        if (rc) return rc;
+      }
     }
   }
   // 4. EMA over all parameters

@@ -48,8 +48,7 @@ class LossPathStep:
             ws_c = lib.b200ssl_cowmix_workspace_bytes(n, h, w)
             ws_l = lib.b200ssl_lovasz_workspace_bytes(C.byref(desc_l))
             self._scratch = {
-                "jgrad": torch.empty_like(scores),
-                "segf": torch.empty(2 * max(n_seg, 1), dtype=torch.float32, device=dev),      # seg_loss | seg_scale
+                "segf": torch.empty(max(n_seg, 1), dtype=torch.float32, device=dev),          # seg_loss
                 "segi": torch.empty(2 * max(n_seg, 1) + n, dtype=torch.int32, device=dev),    # seg_fg | seg_valid | nonzero
                 "ws_c": torch.empty(max(ws_c, 256), dtype=torch.uint8, device=dev),
                 "ws_l": torch.empty(max(ws_l, 256), dtype=torch.uint8, device=dev),
@@ -133,8 +132,8 @@ class LossPathStep:
             small = self._small_init.clone()
             grad = torch.empty_like(scores)
             d.scores, d.target = scores.data_ptr(), target.data_ptr()
-            d.grad, d.small, d.jgrad = grad.data_ptr(), small.data_ptr(), sc["jgrad"].data_ptr()
-            d.seg_loss, d.seg_scale = sc["segf"].data_ptr(), sc["segf"].data_ptr() + 4 * ns
+            d.grad, d.small = grad.data_ptr(), small.data_ptr()
+            d.seg_loss = sc["segf"].data_ptr()
             d.seg_fg, d.seg_valid = sc["segi"].data_ptr(), sc["segi"].data_ptr() + 4 * ns
             d.nonzero = sc["segi"].data_ptr() + 8 * ns
             d.ws_lovasz, d.ws_lovasz_bytes = sc["ws_l"].data_ptr(), sc["ws_l"].numel()

@@ -520,3 +520,32 @@ def test_loss_path_step_softmax_mode(ssl, dev):
     # Lovasz-only entry and a second step reuse the cached scratch
     loss2, grad2, _ = step.lovasz_loss_and_grad(d(probas), d(lab))
     assert float(loss2) == float(out["loss"]) and torch.equal(grad2, out["grad"])
+
+
+@pytest.mark.parametrize("n,c,h,w", [(3, 2, 33, 35), (2, 3, 64, 48), (1, 2, 8, 4), (2, 17, 32, 32)])
+def test_loss_path_step_binary_fused_and_fallback_shapes(ssl, dev, n, c, h, w):
+    """hw % 4 != 0 or C > 16 takes the unfused front end, the others the fused one: same results."""
+    gen = torch.Generator().manual_seed(n * 100 + c * 10 + h)
+    logits = torch.randn(n, c, h, w, generator=gen) * 3
+    lab = coherent_labels(gen, n, c, h, w, 5)
+    lab[0] = 0                                            # an image without foreground: weight 0
+    target = torch.nn.functional.one_hot(lab, c).permute(0, 3, 1, 2).float().contiguous()
+    target = target * 0.9 + 0.05 / c                      # soft one-hot (label smoothing) keeps the argmax
+    step = ssl.LossPathStep(num_classes=c, mode="binary")
+    out = step(None, None, None, None, logits.to(dev), target.to(dev), None, None)
+    o_loss, o_grad = oracle.binary_lovasz_loss_with_logits(logits.numpy(), target.numpy())
+    assert abs(float(out["loss"]) - float(o_loss)) <= REL * abs(float(o_loss)) + 1e-12
+    assert same_nonzero_bits(out["grad"].cpu().numpy(), o_grad)
+    assert np.array_equal(out["labels"].cpu().numpy(), lab.numpy().astype(np.uint8))
+    o_cm, _ = oracle.confusion_matrix(lab.numpy(), logits.argmax(1).numpy(), c, ignore_index=255)
+    assert np.array_equal(out["cm"].cpu().numpy(), o_cm)
+    # separate labels for the matrix (not the Lovasz labels)
+    other = coherent_labels(gen, n, c, h, w, 3)
+    out2 = step(None, None, None, None, logits.to(dev), target.to(dev), None, None, cm_labels=other.to(dev))
+    o_cm2, _ = oracle.confusion_matrix(other.numpy(), logits.argmax(1).numpy(), c, ignore_index=255)
+    assert np.array_equal(out2["cm"].cpu().numpy(), o_cm2)
+    # and the autograd shim gives the same numbers
+    x = logits.to(dev).requires_grad_(True)
+    l2 = ssl.losses.binary_lovasz_loss_with_logits(x, target.to(dev))
+    l2.backward()
+    assert float(l2) == float(out["loss"]) and same_nonzero_bits(x.grad.cpu().numpy(), out["grad"].cpu().numpy())
