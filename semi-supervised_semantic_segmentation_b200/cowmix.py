@@ -23,10 +23,22 @@ def kernel_size_for(sigma_max):
 
 
 _x2_cache = {}
+_range_cache = {}
+_SQRT2 = math.sqrt(2.0)
 
 
-def gaussian_taps(size, sigmas):
-    """All per-sample tap vectors at once: [N, size] fp32 on the CPU.
+def _neg_x2(size):
+    x2 = _x2_cache.get(size)
+    if x2 is None:
+        x = torch.arange(-size // 2, size // 2).float()
+        if size % 2 == 0:
+            x = x + 0.5
+        x2 = _x2_cache[size] = (-x.pow(2.0)).unsqueeze(0)
+    return x2
+
+
+def gaussian_taps(size, sigmas, out=None):
+    """All per-sample tap vectors at once: [N, size] fp32 on the CPU (written into `out` if given).
 
     Batched restatement of cowmix.py:6-24.  For odd `size` the abscissa runs from -(k+1) to k-1
     (the reference's arange(-size//2, size//2)), i.e. the peak sits one tap right of centre.
@@ -34,69 +46,82 @@ def gaussian_taps(size, sigmas):
     use the same inner reduction as its 1-D `gauss.sum()`, so the values are bit-identical to the
     reference's (tests/test_host_logic.py checks this against the golden vectors).
     """
-    x2 = _x2_cache.get(size)
-    if x2 is None:
-        x = torch.arange(-size // 2, size // 2).float()
-        if size % 2 == 0:
-            x = x + 0.5
-        x2 = _x2_cache[size] = (-x.pow(2.0)).unsqueeze(0)
-    denom = 2 * sigmas.float() ** 2                      # float(2 * sigma ** 2) per sample
-    g = torch.exp(x2 / denom.unsqueeze(1))
-    return g / g.sum(1, keepdim=True)
+    denom = sigmas.pow(2).mul_(2)                        # float(2 * sigma ** 2) per sample
+    g = torch.div(_neg_x2(size), denom.unsqueeze(1)).exp_()
+    return torch.div(g, g.sum(1, keepdim=True), out=out)
 
 
 def draw_mask_parameters(n, mask_proportion_range, sigma_range):
     """cowmix.py:44-51: p ~ U(lo,hi), sigma ~ logU(lo,hi), both from the CPU generator, p first.
     `Uniform(lo, hi).rsample([n])` is `lo + torch.rand([n]) * (hi - lo)` on fp32 scalars; issuing
-    those ops directly skips the distribution objects' argument validation (same bits, same RNG use)."""
-    lo, hi = torch.tensor(mask_proportion_range[0]), torch.tensor(mask_proportion_range[1])
-    p = lo + torch.rand([n], dtype=lo.dtype) * (hi - lo)
-    l0 = torch.tensor(math.log(float(sigma_range[0])))
-    l1 = torch.tensor(math.log(float(sigma_range[1])))
-    sigmas = torch.exp(l0 + torch.rand([n], dtype=l0.dtype) * (l1 - l0))
+    those ops directly (in place, with the fp32 constants cached per range) skips the distribution
+    objects and their argument validation -- same bits, same RNG consumption."""
+    key = (mask_proportion_range[0], mask_proportion_range[1], sigma_range[0], sigma_range[1])
+    c = _range_cache.get(key)
+    if c is None:
+        lo, hi = torch.tensor(mask_proportion_range[0]), torch.tensor(mask_proportion_range[1])
+        l0 = torch.tensor(math.log(float(sigma_range[0])))
+        l1 = torch.tensor(math.log(float(sigma_range[1])))
+        if not (lo.dtype == hi.dtype == torch.float32):
+            raise TypeError("mask_proportion_range must be a tuple of python floats")
+        # fp32 values held as python floats: `t * float` and `t + float` round exactly like fp32 tensors
+        c = _range_cache[key] = ((hi - lo).item(), lo.item(), (l1 - l0).item(), l0.item())
+    p = torch.rand([n]).mul_(c[0]).add_(c[1])
+    sigmas = torch.rand([n]).mul_(c[2]).add_(c[3]).exp_()
     return p, sigmas
 
 
 class _Staging:
-    """Ring of pinned host buffers for the per-step taps/factors upload; a slot is reused only after
-    the copy that read it has completed (event per slot), so the host can run ahead of the GPU."""
+    """Ring of pinned host buffers (+ matching device buffers) for the per-step taps/factors upload; a
+    slot is reused only after the copy that read it has completed (event per slot), so the host can
+    run ahead of the GPU and nothing is allocated per step."""
 
-    def __init__(self, slots=8):
-        self.slots = [None] * slots
+    def __init__(self, device, slots=8, floats=64 * 200):
+        self.device = device
+        self.floats = floats
+        self.host = [None] * slots
+        self.dev = [None] * slots
         self.events = [None] * slots
         self.i = 0
 
-    def upload(self, taps, factors, device):
-        n_t, n_f = taps.numel(), factors.numel()
+    def slot(self, n_floats):
         i = self.i
-        self.i = (i + 1) % len(self.slots)
-        buf = self.slots[i]
-        if buf is None or buf.numel() < n_t + n_f:
-            buf = self.slots[i] = torch.empty(max(n_t + n_f, 64 * 200), dtype=torch.float32, pin_memory=True)
+        self.i = (i + 1) % len(self.host)
+        if self.host[i] is None or self.host[i].numel() < n_floats:
+            size = max(n_floats, self.floats)
+            self.host[i] = torch.empty(size, dtype=torch.float32, pin_memory=True)
+            self.dev[i] = torch.empty(size, dtype=torch.float32, device=self.device)
             self.events[i] = torch.cuda.Event()
         else:
             self.events[i].synchronize()
-        buf[:n_t].copy_(taps.reshape(-1))
-        buf[n_t:n_t + n_f].copy_(factors.reshape(-1))
-        dev = buf[:n_t + n_f].to(device, non_blocking=True)
-        self.events[i].record(torch.cuda.current_stream(device))
-        return dev
+        return i
+
+    def upload(self, i, n_floats):
+        d = self.dev[i]
+        d[:n_floats].copy_(self.host[i][:n_floats], non_blocking=True)
+        self.events[i].record(torch.cuda.current_stream(self.device))
+        return d
 
 
 _staging = {}
 
 
 def upload_mask_parameters(p, sigmas, device):
-    """Host part of cowmix.py:27-31 and :64: kernel size, taps and erfinv threshold factors, uploaded
-    in one pinned non-blocking copy.  Returns (size, device buffer [N*size taps | N factors])."""
+    """Host part of cowmix.py:27-31 and :64: kernel size, taps and erfinv threshold factors, computed
+    straight into a pinned staging buffer and uploaded in one non-blocking copy.
+    Returns (size, device buffer [N*size taps | N factors]); the buffer belongs to a ring of 8 and is
+    overwritten 8 calls later (stream-ordered consumers only)."""
+    n = sigmas.shape[0]
     size = kernel_size_for(sigmas.max().item())
-    taps = gaussian_taps(size, sigmas)
-    factors = (torch.erfinv(2 * p - 1) * math.sqrt(2.0)).float()          # cowmix.py:64
-    key = device.index if device.index is not None else torch.cuda.current_device()
-    st = _staging.get(key)
+    st = _staging.get(device)
     if st is None:
-        st = _staging[key] = _Staging()
-    return size, st.upload(taps, factors, device)
+        st = _staging[device] = _Staging(device)
+    i = st.slot(n * size + n)
+    host = st.host[i]
+    gaussian_taps(size, sigmas.float(), out=host[: n * size].view(n, size))
+    # cowmix.py:64  torch.erfinv(2 * p - 1) * math.sqrt(2.0)
+    torch.mul(p.mul(2).sub_(1).erfinv_(), _SQRT2, out=host[n * size: n * size + n])
+    return size, st.upload(i, n * size + n)
 
 
 def masks_from_noise(noise, p, sigmas, return_field=False):
