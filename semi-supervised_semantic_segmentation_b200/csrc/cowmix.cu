@@ -15,13 +15,13 @@
 //     C oracle (oracle/oracle.c) does exactly the same and matches bit for bit.
 //   * Statistics are accumulated in fp64 per thread and reduced in a fixed order (deterministic).
 //
-// Fast path (conv_tma_tile_kernel): the input tile of a 64x64 output block -- (64 + K - 1) rows of
+// Fast path (conv_tma_tile_kernel): the input tile of a 64-row x 64-column output block -- (64 + K - 1) rows of
 // 64 columns -- is brought into shared memory by TMA (cp.async.bulk.tensor, 32-row boxes, one
 // mbarrier per box so the first rows can be consumed while the rest is in flight).  TMA zero-fills
 // rows/columns outside the image, which IS the convolution's zero padding, so the inner loop has
 // no bounds checks at all: per input row one 8-byte shared load of the data pair, one broadcast
 // 8-byte load of the duplicated tap, 16 FFMA2.  The four warps of a block share the tile (read
-// amplification (64+K-1)/64 instead of (16+K-1)/16 from L2).  Needs a 16-byte aligned base and a
+// amplification (64+K-1)/64 instead of (16+K-1)/16 from L2; eight warps x 128 rows measured slower).  Needs a 16-byte aligned base and a
 // fast-axis extent that is a multiple of 4 (tensor-map stride rule); other shapes take the generic
 // kernel below, which produces bit-identical results.
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
@@ -38,7 +38,8 @@ constexpr int kTileCols = 64;                       // fast-axis columns per blo
 constexpr int kTileWarps = 4;
 constexpr int kTileRowsOut = kTileWarps * kConvR;   // 64 output rows per block
 constexpr int kBoxRows = 32;                        // rows per TMA box / mbarrier
-constexpr int kMaxBoxes = 8;                        // 256 staged rows: enough for K <= 193
+constexpr int kMaxBoxes = 10;                       // 320 staged rows: enough for K <= 193
+constexpr int kTileHeadBytes = 128;                 // mbarriers in front of the taps and the tile
 constexpr int kBoxBytes = kBoxRows * kTileCols * 4; // 8 KiB
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
@@ -78,9 +79,10 @@ conv_tma_tile_kernel(const __grid_constant__ CUtensorMap in_map, float* __restri
                      double* __restrict__ partials) {
   constexpr int R = kConvR;
   extern __shared__ __align__(128) unsigned char conv_smem[];
-  float* tile = reinterpret_cast<float*>(conv_smem);                                   // [boxes*32][64]
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(conv_smem + kMaxBoxes * kBoxBytes);
-  float2* wdup = reinterpret_cast<float2*>(conv_smem + kMaxBoxes * kBoxBytes + 64);     // [K + 3R]
+  // layout: [mbarriers, 128 B][duplicated taps, (K + 3R) float2 rounded up to 128 B][n_boxes x 8 KiB tile]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(conv_smem);
+  float2* wdup = reinterpret_cast<float2*>(conv_smem + kTileHeadBytes);                 // [K + 3R]
+  float* tile = reinterpret_cast<float*>(conv_smem + kTileHeadBytes + (((K + 3 * kConvR) * 8 + 127) / 128) * 128);
 
   const int n = blockIdx.z;
   const int k = K >> 1;
@@ -426,11 +428,14 @@ static int launch_conv_tma(const float* in, float* out, const float* taps, int K
     set_error("%s: cuTensorMapEncodeTiled failed (%d)", name, (int)r);
     return B200SSL_EUNSUPPORTED;
   }
-  const size_t smem = (size_t)kMaxBoxes * kBoxBytes + 64 + (size_t)(K + 3 * kConvR) * sizeof(float2);
+  const int groups = (kConvR + K - 1 + kConvR - 1) / kConvR;
+  const int n_boxes = ((kTileWarps - 1) * kConvR + groups * kConvR + kBoxRows - 1) / kBoxRows;
+  const size_t smem = (size_t)kTileHeadBytes + (((size_t)(K + 3 * kConvR) * 8 + 127) / 128) * 128 + (size_t)n_boxes * kBoxBytes;
   auto kern = conv_tma_tile_kernel<STATS>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxBoxes * kBoxBytes + 64 + (193 + 3 * kConvR) * sizeof(float2)));
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(kTileHeadBytes + (((193 + 3 * kConvR) * 8 + 127) / 128) * 128 + kMaxBoxes * kBoxBytes));
     attr_done = true;
   }
   const ConvGrid g = conv_tma_grid(n, A, B);

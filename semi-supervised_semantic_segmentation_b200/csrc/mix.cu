@@ -9,7 +9,7 @@
 namespace b200ssl {
 
 constexpr int kMixThreads = 256;
-constexpr int kMixChanUnroll = 4;
+constexpr int kMixChanUnroll = 2;
 
 // RN(RN(a*m) + RN(b*RN(1-m))): the exact op sequence of `a*mask + b*(1.-mask)`; no FMA contraction.
 __device__ __forceinline__ float mix_one(float a, float b, float m, float om) {
@@ -69,7 +69,7 @@ __device__ __forceinline__ void mix_tensor(const float* __restrict__ a, const fl
 }
 
 template <int VEC, bool CHANNEL_MASK>
-__global__ void __launch_bounds__(kMixThreads)
+__global__ void __launch_bounds__(kMixThreads, 4)
 mix2_kernel(const float* __restrict__ a0, const float* __restrict__ b0, float* __restrict__ out0,
             int c0, const float* __restrict__ a1, const float* __restrict__ b1,
             float* __restrict__ out1, int c1, const float* __restrict__ mask, long long n,
