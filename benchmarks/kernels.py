@@ -1,0 +1,116 @@
+#!/usr/bin/env python
+"""Stand-alone timings of the path's kernels on the other BASELINE.json configs (parity-test shapes,
+not the bench.py line): confusion-matrix sweep (configs[4]), EMA parameter sets (configs[2], [3]),
+multi-class Lovasz (configs[2], [3] shapes at a reduced batch) and the mix at 19/21 classes.
+Prints one JSON object; CUDA-event timing, median of `reps` after warm-up, inputs larger than L2 or
+rotated across buffers.   python benchmarks/kernels.py [--quick]"""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import b200ssl  # noqa: E402
+import bench    # noqa: E402
+
+dev = torch.device("cuda:0")
+PEAK, _ = bench.measured_peak()
+
+
+def timeit(fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def coherent(n, c, h, w, gen):
+    x = torch.randn(n, c, h // 8, w // 8, device=dev, generator=gen)
+    x = torch.nn.functional.interpolate(x, size=(h, w), mode="bilinear")
+    return x.argmax(1)
+
+
+def main():
+    quick = "--quick" in sys.argv
+    gen = torch.Generator(device=dev).manual_seed(0)
+    out = {"peak_GBps": PEAK}
+
+    # ---- configs[4]: 19-class confusion matrix over 1024x2048 masks, chunks of 32 masks (> L2)
+    n, h, w, c = 32, 1024, 2048, 19
+    lab = coherent(n, c, h, w, gen)
+    prd = coherent(n, c, h, w, gen)
+    lab[torch.rand(n, h, w, device=dev, generator=gen) < 0.03] = 255
+    for dt, name in [(torch.int64, "int64"), (torch.uint8, "uint8")]:
+        l, p = lab.to(dt), prd.to(dt)
+        acc = torch.zeros(c, c, dtype=torch.int64, device=dev)
+        ms = timeit(lambda: b200ssl.metrics.confusion_matrix(l, p, c, ignore_index=255, out=acc))
+        bytes_ = 2 * l.numel() * l.element_size()
+        out[f"cm_{name}_19c_32x1024x2048"] = {"ms": round(ms, 4), "Gpix_s": round(l.numel() / ms / 1e6, 2),
+                                             "GBps": round(bytes_ / ms / 1e6, 1), "frac": round(bytes_ / ms / 1e6 / PEAK, 3)}
+    logits = torch.randn(8, c, h, w, device=dev, generator=gen)
+    l8 = lab[:8].to(torch.uint8)
+    ms = timeit(lambda: b200ssl.metrics.confusion_matrix_from_logits(logits, l8, ignore_index=255))
+    bytes_ = logits.numel() * 4 + l8.numel()
+    out["cm_from_logits_19c_8x1024x2048"] = {"ms": round(ms, 4), "GBps": round(bytes_ / ms / 1e6, 1),
+                                             "frac": round(bytes_ / ms / 1e6 / PEAK, 3)}
+    del logits, lab, prd
+
+    # ---- EMA parameter sets
+    for key in ["unet_mnv2_c2", "simple_unet_c2", "deeplabv3_r101_c21"]:
+        shapes = bench.load_param_shapes(key)
+        ps = [torch.randn(s, device=dev, generator=gen) for s in shapes]
+        es = [torch.randn(s, device=dev, generator=gen) for s in shapes]
+        upd = b200ssl.mean_teacher.EmaUpdater()
+        ms = timeit(lambda: upd(es, ps, 0.99))
+        npar = sum(p.numel() for p in ps)
+        out[f"ema_{key}"] = {"params": npar, "tensors": len(ps), "ms": round(ms, 4),
+                             "GBps": round(12 * npar / ms / 1e6, 1), "frac": round(12 * npar / ms / 1e6 / PEAK, 3)}
+        # the reference's own op sequence on the same GPU (2 launches per tensor)
+        def ref():
+            for e, p in zip(es, ps):
+                e.mul_(0.99).add_(p, alpha=1 - 0.99)
+        ms_ref = timeit(ref, reps=5, warm=1)
+        out[f"ema_{key}"]["torch_cuda_ref_ms"] = round(ms_ref, 4)
+        del ps, es
+
+    # ---- multi-class Lovasz forward+backward (fused), configs[2]/[3] class counts
+    for (n, c, h, w) in ([(4, 21, 512, 512)] if quick else [(4, 21, 512, 512), (1, 19, 1024, 2048)]):
+        probas = torch.softmax(torch.randn(n, c, h, w, device=dev, generator=gen) * 2, 1)
+        labels = coherent(n, c, h, w, gen)
+        labels[torch.rand(n, h, w, device=dev, generator=gen) < 0.03] = 255
+        step = b200ssl.LossPathStep(num_classes=c, mode="softmax", classes="present", per_image=False, ignore=255)
+        ms = timeit(lambda: step.lovasz_loss_and_grad(probas, labels), reps=10)
+        P = n * h * w
+        alg = (8 * c + 8) * P
+        out[f"lovasz_softmax_present_{n}x{c}x{h}x{w}"] = {"ms": round(ms, 4), "Mpix_s": round(P / ms / 1e3, 1),
+                                                       "alg_GBps": round(alg / ms / 1e6, 1),
+                                                       "frac": round(alg / ms / 1e6 / PEAK, 3),
+                                                       "Gkeys_s": round(P * c / ms / 1e6, 2)}
+        del probas, labels
+
+    # ---- fused mix at 21 classes (configs[2]) 8x512x512
+    n, c, h, w = 8, 21, 512, 512
+    ia, ib = (torch.rand(n, 3, h, w, device=dev, generator=gen) for _ in range(2))
+    ta, tb = (torch.randn(n, c, h, w, device=dev, generator=gen) for _ in range(2))
+    mask = (torch.rand(n, 1, h, w, device=dev, generator=gen) > 0.5).float()
+    ms = timeit(lambda: b200ssl.cowmix.mix2_with_mask(ia, ib, ta, tb, mask))
+    bytes_ = 4 * (3 * 3 + 3 * c + 1) * n * h * w
+    out[f"mix2_{n}x{c}x{h}x{w}"] = {"ms": round(ms, 4), "GBps": round(bytes_ / ms / 1e6, 1),
+                                    "frac": round(bytes_ / ms / 1e6 / PEAK, 3)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -90,6 +90,36 @@ __device__ __forceinline__ void warp_run_add(unsigned* hist, int bin) {
   }
 }
 
+// As warp_run_add, but every contributing lane stands for `weight` identical elements.
+__device__ __forceinline__ void warp_run_add_weighted(unsigned* hist, int bin, unsigned weight) {
+  const unsigned lane = lane_id();
+  const int prev = __shfl_up_sync(0xffffffffu, bin, 1);
+  const bool head = (lane == 0) || (bin != prev);
+  const unsigned heads = __ballot_sync(0xffffffffu, head);
+  if (head && bin >= 0) {
+    const unsigned later = (lane == 31) ? 0u : (heads & (0xffffffffu << (lane + 1)));
+    const int end = later ? (__ffs(later) - 1) : 32;
+    atomicAdd(hist + bin, (unsigned)(end - (int)lane) * weight);
+  }
+}
+
+// N consecutive elements per lane (labels are spatially coherent, so the N bins of a lane almost
+// always agree): lanes whose N bins are equal go through ONE warp-merged atomic with weight N, the
+// others fall back to one atomic per element.  Warp-collective: call with all 32 lanes.
+template <int N>
+__device__ __forceinline__ void lane_run_add(unsigned* hist, const int (&bin)[N]) {
+  bool uniform = true;
+#pragma unroll
+  for (int e = 1; e < N; ++e) uniform = uniform && (bin[e] == bin[0]);
+  warp_run_add_weighted(hist, uniform ? bin[0] : -1, (unsigned)N);
+  if (!uniform) {
+#pragma unroll
+    for (int e = 0; e < N; ++e)
+      if (bin[e] >= 0) atomicAdd(hist + bin[e], 1u);
+  }
+}
+__device__ __forceinline__ void quad_run_add(unsigned* hist, const int (&bin)[4]) { lane_run_add<4>(hist, bin); }
+
 // labels come as int64 (torch default), int32 or uint8; always widened to int64 for compares
 template <int DT>
 struct LabelT;

@@ -101,26 +101,31 @@ confusion_kernel(const T* __restrict__ labels, const T* __restrict__ preds, long
       const long long g = g0 + (long long)u * kCmWarps;
       if (g >= g_end) break;  // warp-uniform
       const long long first = (g * 32 + lane_id()) * ELEMS;
+      int bin[ELEMS];
 #pragma unroll
       for (int e = 0; e < ELEMS; ++e) {
-        int bin = -1;
+        bin[e] = -1;
         if (full[u]) {
-          bin = make_bin<T>(lv[u].e[e], pv[u].e[e], C, D, has_ignore, ignore, dropped);
+          bin[e] = make_bin<T>(lv[u].e[e], pv[u].e[e], C, D, has_ignore, ignore, dropped);
         } else if (first + e < plane_pixels) {  // ragged tail of the plane: scalar loads
-          bin = make_bin<T>(labels[first + e], preds[first + e], C, D, has_ignore, ignore, dropped);
+          bin[e] = make_bin<T>(labels[first + e], preds[first + e], C, D, has_ignore, ignore, dropped);
         }
-        if (use_smem) {
-          warp_run_add(my_hist, bin);
-        } else {
-          // very large C: the matrix does not fit in shared memory, merge runs then go to L2
+      }
+      if (use_smem) {
+        // the ELEMS pixels of a lane almost always share a bin: one warp-merged atomic per lane group
+        lane_run_add<ELEMS>(my_hist, bin);
+      } else {
+        // very large C: the matrix does not fit in shared memory, merge runs then go to L2
+#pragma unroll
+        for (int e = 0; e < ELEMS; ++e) {
           const unsigned lane = lane_id();
-          const int prev = __shfl_up_sync(0xffffffffu, bin, 1);
-          const bool head = (lane == 0) || (bin != prev);
+          const int prev = __shfl_up_sync(0xffffffffu, bin[e], 1);
+          const bool head = (lane == 0) || (bin[e] != prev);
           const unsigned heads = __ballot_sync(0xffffffffu, head);
-          if (head && bin >= 0) {
+          if (head && bin[e] >= 0) {
             const unsigned later = (lane == 31) ? 0u : (heads & (0xffffffffu << (lane + 1)));
             const int end = later ? (__ffs(later) - 1) : 32;
-            atomicAdd(cm + bin, (unsigned long long)(end - (int)lane));
+            atomicAdd(cm + bin[e], (unsigned long long)(end - (int)lane));
           }
         }
       }
@@ -199,19 +204,17 @@ confusion_logits_kernel(const float* __restrict__ logits, const T* __restrict__ 
         }
       }
     }
+    int bin[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      int bin = -1;
+      bin[e] = -1;
       if (first + e < hw) {
-        bin = make_bin<long long>((long long)labels[first + e], (long long)arg[e], C, D, has_ignore,
-                                  ignore, dropped);
+        bin[e] = make_bin<long long>((long long)labels[first + e], (long long)arg[e], C, D, has_ignore,
+                                     ignore, dropped);
       }
-      if (use_smem) {
-        warp_run_add(my_hist, bin);
-      } else if (bin >= 0) {
-        atomicAdd(cm + bin, 1ull);
-      }
+      if (!use_smem && bin[e] >= 0) atomicAdd(cm + bin[e], 1ull);
     }
+    if (use_smem) lane_run_add<4>(my_hist, bin);
   }
   if (dropped_out) {
     const unsigned d = warp_sum(dropped);
