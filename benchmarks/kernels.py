@@ -20,7 +20,9 @@ dev = torch.device("cuda:0")
 PEAK, _ = bench.measured_peak()
 
 
-def timeit(fn, reps=20, warm=3):
+def timeit(fn, reps=10, warm=3, inner=10):
+    """median over `reps` of (CUDA-event time of `inner` back-to-back calls) / inner: the queue stays
+    full, so host launch latency does not leak into short kernels"""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -28,16 +30,18 @@ def timeit(fn, reps=20, warm=3):
     for _ in range(reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        for _ in range(inner):
+            fn()
         b.record()
         b.synchronize()
-        ts.append(a.elapsed_time(b))
+        ts.append(a.elapsed_time(b) / inner)
     ts.sort()
     return ts[len(ts) // 2]
 
 
 def coherent(n, c, h, w, gen):
-    x = torch.randn(n, c, h // 8, w // 8, device=dev, generator=gen)
+    """spatially coherent label maps (argmax of noise blurred at ~16 px)"""
+    x = torch.randn(n, c, h // 32, w // 32, device=dev, generator=gen)
     x = torch.nn.functional.interpolate(x, size=(h, w), mode="bilinear")
     return x.argmax(1)
 
@@ -50,8 +54,9 @@ def main():
     # ---- configs[4]: 19-class confusion matrix over 1024x2048 masks, chunks of 32 masks (> L2)
     n, h, w, c = 32, 1024, 2048, 19
     lab = coherent(n, c, h, w, gen)
-    prd = coherent(n, c, h, w, gen)
-    lab[torch.rand(n, h, w, device=dev, generator=gen) < 0.03] = 255
+    wrong = coherent(n, 5, h, w, gen) == 0                      # ~20 % of the area, in blobs
+    prd = torch.where(wrong, coherent(n, c, h, w, gen), lab)    # predictions agree except in blobs
+    lab[coherent(n, 30, h, w, gen) == 0] = 255                  # ~3 % void, in blobs
     for dt, name in [(torch.int64, "int64"), (torch.uint8, "uint8")]:
         l, p = lab.to(dt), prd.to(dt)
         acc = torch.zeros(c, c, dtype=torch.int64, device=dev)
@@ -81,7 +86,7 @@ def main():
         def ref():
             for e, p in zip(es, ps):
                 e.mul_(0.99).add_(p, alpha=1 - 0.99)
-        ms_ref = timeit(ref, reps=5, warm=1)
+        ms_ref = timeit(ref, reps=3, warm=1, inner=2)
         out[f"ema_{key}"]["torch_cuda_ref_ms"] = round(ms_ref, 4)
         del ps, es
 
@@ -91,7 +96,7 @@ def main():
         labels = coherent(n, c, h, w, gen)
         labels[torch.rand(n, h, w, device=dev, generator=gen) < 0.03] = 255
         step = b200ssl.LossPathStep(num_classes=c, mode="softmax", classes="present", per_image=False, ignore=255)
-        ms = timeit(lambda: step.lovasz_loss_and_grad(probas, labels), reps=10)
+        ms = timeit(lambda: step.lovasz_loss_and_grad(probas, labels), reps=5, inner=4)
         P = n * h * w
         alg = (8 * c + 8) * P
         out[f"lovasz_softmax_present_{n}x{c}x{h}x{w}"] = {"ms": round(ms, 4), "Mpix_s": round(P / ms / 1e3, 1),

@@ -261,6 +261,24 @@ int b200ssl_dice_from_cm(const long long* cm_per_image, int n_images, float* dic
                          b200ssl_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Confidence-masked consistency loss of the semi-supervised branch ("next" row N1), reference
+ * train.py:98-107 (inline code) and autograd's backward w.r.t. the student logits:
+ *     t = sigmoid(teacher), s = sigmoid(student)                      [n, c, hw] fp32 logits
+ *     conf = (max_c t > threshold) ? 1 : 0
+ *     loss = sum_pixels(sum_c (s-t)^2 * conf) / sum(conf)             (NaN if no pixel is confident)
+ * forward : stats_out[0] = loss, [1] = sum(conf), [2] = mean(conf)    (one pass, 8 B/element)
+ * backward: grad_student = grad_out * 2 (s-t) conf / sum(conf) * s (1-s)   (12 B/element);
+ *           `stats` is the forward's stats_out, grad_out a device scalar.
+ * --------------------------------------------------------------------------------------------- */
+size_t b200ssl_consistency_workspace_bytes(int n, int64_t hw);
+int b200ssl_consistency_forward(const float* student, const float* teacher, int n, int c, int64_t hw,
+                                float threshold, float* stats_out, void* workspace, size_t workspace_bytes,
+                                b200ssl_stream_t stream);
+int b200ssl_consistency_backward(const float* student, const float* teacher, int n, int c, int64_t hw,
+                                 float threshold, const float* stats, const float* grad_out,
+                                 float* grad_student, b200ssl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * The whole loss path of one semi-supervised step in one call (train.py:65-130 order): mask, fused
  * mix of images + teacher predictions, Lovasz forward/backward (unit upstream gradient), EMA,
  * confusion matrix of (labels, argmax scores).  Chains the entry points above on `stream`; any stage

@@ -205,6 +205,18 @@ def confusion_matrix(labels, preds, num_classes, ignore_index=None):
     return torch.bincount(lab * num_classes + pr, minlength=num_classes * num_classes).view(num_classes, num_classes)
 
 
+# ---------------------------------------------------------------- train.py:98-107 ----------------
+def confidence_masked_consistency(student_logits, teacher_logits, confidence_threshold):
+    """The inline consistency-loss code of train.py:98-107 as a function: returns
+    (consistency_loss, confidence_modulator.mean())."""
+    t = torch.sigmoid(teacher_logits)
+    s = torch.sigmoid(student_logits)
+    conf = (t.max(dim=1).values > confidence_threshold).to(t)
+    sq = torch.pow(s - t, exponent=2.0)
+    loss = (sq.sum(dim=1) * conf).sum() / conf.sum()
+    return loss.mean(), conf.mean()
+
+
 # ---------------------------------------------------------------- whole step (bench baseline) ----
 def loss_path_step(image_a, image_b, teacher_a, teacher_b, scores, target, params, ema_params,
                    mode="binary", mask_proportion_range=(0.45, 0.55), sigma_range=(8, 32), alpha=0.99,

@@ -37,6 +37,23 @@ __device__ __forceinline__ int make_bin(T l, T p, int C, int D, bool has_ignore,
   return (int)ll * D + (int)pp;
 }
 
+// same for labels that fit 32 bits (uint8 / int32 inputs): no 64-bit compares on the hot path.
+// ignore32 is the ignore index if it is representable, else a value no label can take.
+__device__ __forceinline__ int make_bin32(int l, int p, int C, int D, bool has_ignore, int ignore32,
+                                          unsigned& dropped) {
+  if (has_ignore && l == ignore32) return -1;
+  const bool lo = ((unsigned)l >= (unsigned)C), po = ((unsigned)p >= (unsigned)C);
+  if (lo || po) {
+    if (D == C) {
+      ++dropped;
+      return -1;
+    }
+    if (lo) l = C;
+    if (po) p = C;
+  }
+  return l * D + p;
+}
+
 // flush a block's private copies into the global int64 matrix
 __device__ __forceinline__ void flush_hist(const unsigned* hist, int copies, int bins,
                                            unsigned long long* cm) {
@@ -101,6 +118,73 @@ confusion_kernel(const T* __restrict__ labels, const T* __restrict__ preds, long
       const long long g = g0 + (long long)u * kCmWarps;
       if (g >= g_end) break;  // warp-uniform
       const long long first = (g * 32 + lane_id()) * ELEMS;
+      // Packed labels (4 x int32 / 16 x uint8 per lane): a lane whose ELEMS labels and ELEMS
+      // predictions are all equal -- the normal case inside a segment -- computes ONE bin and adds it
+      // with weight ELEMS through the warp-merged path; only lanes that straddle a boundary (or the
+      // ragged tail) fall back to one bin and one atomic per element.
+      if (ELEMS >= 4 && use_smem) {
+        bool lane_uniform = false;
+        if (full[u]) {
+          unsigned l0 = lv[u].u.x, p0 = pv[u].u.x;
+          if (sizeof(T) == 1) { l0 = (l0 & 0xffu) * 0x01010101u; p0 = (p0 & 0xffu) * 0x01010101u; }
+          lane_uniform = lv[u].u.x == l0 && lv[u].u.y == l0 && lv[u].u.z == l0 && lv[u].u.w == l0 &&
+                         pv[u].u.x == p0 && pv[u].u.y == p0 && pv[u].u.z == p0 && pv[u].u.w == p0;
+        }
+        int b = -1;
+        if (lane_uniform) {
+          unsigned d1 = 0;
+          b = make_bin<T>(lv[u].e[0], pv[u].e[0], C, D, has_ignore, ignore, d1);
+          dropped += d1 * ELEMS;
+        }
+        warp_run_add_weighted(my_hist, b, (unsigned)ELEMS);
+        if (!lane_uniform) {
+          // boundary lane (or ragged tail): run-length merge inside the lane, 32-bit arithmetic
+          const bool ign_fits = ignore >= -2147483647ll && ignore <= 2147483647ll;
+          const int ignore32 = ign_fits ? (int)ignore : (int)0x80000000;
+          const bool has_ign32 = has_ignore && ign_fits;
+          int cur = -1;
+          unsigned cnt = 0;
+          auto merge = [&](int be, unsigned n) {
+            if (be == cur) {
+              cnt += n;
+            } else {
+              if (cur >= 0) atomicAdd(my_hist + cur, cnt);
+              cur = be;
+              cnt = n;
+            }
+          };
+          if (full[u]) {
+            // word by word: a uint8 word holds 4 pixels that mostly agree even in a boundary lane
+            const unsigned lw[4] = {lv[u].u.x, lv[u].u.y, lv[u].u.z, lv[u].u.w};
+            const unsigned pw[4] = {pv[u].u.x, pv[u].u.y, pv[u].u.z, pv[u].u.w};
+#pragma unroll
+            for (int w4 = 0; w4 < 4; ++w4) {
+              if (sizeof(T) == 1) {
+                const unsigned l0 = lw[w4] & 0xffu, p0 = pw[w4] & 0xffu;
+                if (lw[w4] == l0 * 0x01010101u && pw[w4] == p0 * 0x01010101u) {
+                  unsigned d1 = 0;
+                  const int be = make_bin32((int)l0, (int)p0, C, D, has_ign32, ignore32, d1);
+                  dropped += 4u * d1;
+                  merge(be, 4u);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    merge(make_bin32((int)((lw[w4] >> (8 * e)) & 0xffu), (int)((pw[w4] >> (8 * e)) & 0xffu), C, D,
+                                     has_ign32, ignore32, dropped), 1u);
+                }
+              } else {
+                merge(make_bin32((int)lw[w4], (int)pw[w4], C, D, has_ign32, ignore32, dropped), 1u);
+              }
+            }
+          } else {
+            for (int e = 0; e < ELEMS; ++e)
+              if (first + e < plane_pixels)
+                merge(make_bin32((int)labels[first + e], (int)preds[first + e], C, D, has_ign32, ignore32, dropped), 1u);
+          }
+          if (cur >= 0) atomicAdd(my_hist + cur, cnt);
+        }
+        continue;
+      }
       int bin[ELEMS];
 #pragma unroll
       for (int e = 0; e < ELEMS; ++e) {

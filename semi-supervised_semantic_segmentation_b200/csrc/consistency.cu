@@ -1,0 +1,211 @@
+// Confidence-masked consistency loss of the semi-supervised branch, forward and backward
+// ("next" row N1 of SURVEY 8f).  Reference semantics: train.py:98-107 (inline code):
+//     t = sigmoid(mixed_ema_pred);  s = sigmoid(mixed_student_pred)
+//     conf = (t.max(dim=1).values > confidence_threshold).to(t)                      [N,H,W]
+//     loss = (pow(s - t, 2).sum(dim=1) * conf).sum() / conf.sum();  conf_mean = conf.mean()
+// and autograd's backward w.r.t. the student logits:
+//     d loss / d x[n,c,i] = go * 2 (s - t) * conf[n,i] / conf.sum() * s (1 - s)
+// The reference runs ~12 elementwise/reduction kernels with 6 full-size temporaries; here the forward
+// is ONE pass over both logit tensors (8 B/element) and the backward one more (12 B/element).
+//
+// Roofline: HBM-bound.  Sums are accumulated in fp64 and reduced in a fixed order (deterministic).
+#include "common.cuh"
+
+namespace b200ssl {
+
+constexpr int kConsThreads = 256;
+
+__device__ __forceinline__ float sigmoidf_rn(float x) {
+  // 1 / (1 + exp(-x)) with IEEE division; expf is the accurate (non fast-math) version
+  return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+}
+
+// grid = (blocks, n): each thread walks quads of pixels of image n, all C channels per quad
+__global__ void __launch_bounds__(kConsThreads)
+consistency_partial_kernel(const float* __restrict__ student, const float* __restrict__ teacher, int C,
+                           long long hw, float thr, double* __restrict__ partials, bool vec) {
+  const int n = blockIdx.y;
+  const float* __restrict__ sp = student + (long long)n * C * hw;
+  const float* __restrict__ tp = teacher + (long long)n * C * hw;
+  double s_conf = 0.0, s_loss = 0.0;
+  const long long quads = (hw + 3) / 4;
+  for (long long q = (long long)blockIdx.x * kConsThreads + threadIdx.x; q < quads;
+       q += (long long)gridDim.x * kConsThreads) {
+    const long long i0 = q * 4;
+    float tmax[4] = {-1.f, -1.f, -1.f, -1.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool full = vec && (i0 + 4 <= hw);
+    for (int c = 0; c < C; ++c) {
+      float sv[4] = {0.f, 0.f, 0.f, 0.f}, tv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (full) {
+        const float4 a = ld_stream_f4(sp + (long long)c * hw + i0);
+        const float4 b = ld_stream_f4(tp + (long long)c * hw + i0);
+        sv[0] = a.x; sv[1] = a.y; sv[2] = a.z; sv[3] = a.w;
+        tv[0] = b.x; tv[1] = b.y; tv[2] = b.z; tv[3] = b.w;
+      } else {
+        for (int e = 0; e < 4; ++e)
+          if (i0 + e < hw) { sv[e] = sp[(long long)c * hw + i0 + e]; tv[e] = tp[(long long)c * hw + i0 + e]; }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float s = sigmoidf_rn(sv[e]), t = sigmoidf_rn(tv[e]);
+        const float d = __fsub_rn(s, t);
+        sq[e] = __fadd_rn(sq[e], __fmul_rn(d, d));          // pow(.,2).sum(dim=1): channels in order
+        tmax[e] = fmaxf(tmax[e], t);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (i0 + e < hw && tmax[e] > thr) {
+        s_conf += 1.0;
+        s_loss += (double)sq[e];
+      }
+    }
+  }
+  __shared__ double red[2][kConsThreads / 32];
+  s_conf = warp_sum(s_conf);
+  s_loss = warp_sum(s_loss);
+  if (lane_id() == 0) { red[0][threadIdx.x >> 5] = s_conf; red[1][threadIdx.x >> 5] = s_loss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < kConsThreads / 32; ++w) { a += red[0][w]; b += red[1][w]; }
+    const long long blk = (long long)n * gridDim.x + blockIdx.x;
+    partials[2 * blk + 0] = a;
+    partials[2 * blk + 1] = b;
+  }
+}
+
+// stats[0] = loss, stats[1] = conf.sum(), stats[2] = conf.mean()
+__global__ void consistency_final_kernel(const double* __restrict__ partials, int n_partials, double n_pixels,
+                                         float* __restrict__ stats) {
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < n_partials; i += 32) { a += partials[2 * i]; b += partials[2 * i + 1]; }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (threadIdx.x == 0) {
+    const float conf_sum = (float)a;
+    stats[0] = __fdiv_rn((float)b, conf_sum);      // 0/0 = NaN when no pixel is confident, as the reference
+    stats[1] = conf_sum;
+    stats[2] = (float)(a / n_pixels);
+  }
+}
+
+__global__ void __launch_bounds__(kConsThreads)
+consistency_grad_kernel(const float* __restrict__ student, const float* __restrict__ teacher, int C, long long hw,
+                        float thr, const float* __restrict__ stats, const float* __restrict__ grad_out,
+                        float* __restrict__ grad, bool vec) {
+  const int n = blockIdx.y;
+  const float* __restrict__ sp = student + (long long)n * C * hw;
+  const float* __restrict__ tp = teacher + (long long)n * C * hw;
+  float* __restrict__ gp = grad + (long long)n * C * hw;
+  // autograd: DivBackward -> go / conf_sum ; MulBackward (* conf) ; PowBackward 2 * d ; SigmoidBackward s (1 - s)
+  const float scale = __fdiv_rn(grad_out[0], stats[1]);
+  const long long quads = (hw + 3) / 4;
+  for (long long q = (long long)blockIdx.x * kConsThreads + threadIdx.x; q < quads;
+       q += (long long)gridDim.x * kConsThreads) {
+    const long long i0 = q * 4;
+    const bool full = vec && (i0 + 4 <= hw);
+    // pass 1 over the channels: confidence of the 4 pixels (teacher only)
+    float tmax[4] = {-1.f, -1.f, -1.f, -1.f};
+    for (int c = 0; c < C; ++c) {
+      if (full) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(tp + (long long)c * hw + i0));
+        tmax[0] = fmaxf(tmax[0], b.x); tmax[1] = fmaxf(tmax[1], b.y);
+        tmax[2] = fmaxf(tmax[2], b.z); tmax[3] = fmaxf(tmax[3], b.w);
+      } else {
+        for (int e = 0; e < 4; ++e)
+          if (i0 + e < hw) tmax[e] = fmaxf(tmax[e], tp[(long long)c * hw + i0 + e]);
+      }
+    }
+    float conf[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) conf[e] = sigmoidf_rn(tmax[e]) > thr ? 1.0f : 0.0f;  // sigmoid is monotone
+    // pass 2: gradient per channel (teacher planes come back from L1/L2)
+    for (int c = 0; c < C; ++c) {
+      float sv[4] = {0.f, 0.f, 0.f, 0.f}, tv[4] = {0.f, 0.f, 0.f, 0.f}, g[4];
+      if (full) {
+        const float4 a = ld_stream_f4(sp + (long long)c * hw + i0);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(tp + (long long)c * hw + i0));
+        sv[0] = a.x; sv[1] = a.y; sv[2] = a.z; sv[3] = a.w;
+        tv[0] = b.x; tv[1] = b.y; tv[2] = b.z; tv[3] = b.w;
+      } else {
+        for (int e = 0; e < 4; ++e)
+          if (i0 + e < hw) { sv[e] = sp[(long long)c * hw + i0 + e]; tv[e] = tp[(long long)c * hw + i0 + e]; }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float s = sigmoidf_rn(sv[e]), t = sigmoidf_rn(tv[e]);
+        const float d = __fsub_rn(s, t);
+        const float up = __fmul_rn(__fmul_rn(scale, conf[e]), __fmul_rn(2.0f, d));
+        g[e] = __fmul_rn(up, __fmul_rn(s, __fsub_rn(1.0f, s)));
+      }
+      if (full) {
+        st_stream_f4(gp + (long long)c * hw + i0, make_float4(g[0], g[1], g[2], g[3]));
+      } else {
+        for (int e = 0; e < 4; ++e)
+          if (i0 + e < hw) gp[(long long)c * hw + i0 + e] = g[e];
+      }
+    }
+  }
+}
+
+static int cons_blocks(int n, long long hw) {
+  long long bx = ((hw + 3) / 4 + kConsThreads - 1) / kConsThreads;
+  long long cap = (long long)kNumSMs * 8 / (n > 0 ? n : 1);
+  if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  return (int)bx;
+}
+
+}  // namespace b200ssl
+
+extern "C" {
+
+size_t b200ssl_consistency_workspace_bytes(int n, int64_t hw) {
+  if (n <= 0 || hw <= 0) return 0;
+  return (size_t)n * b200ssl::cons_blocks(n, hw) * 2 * sizeof(double);
+}
+
+int b200ssl_consistency_forward(const float* student, const float* teacher, int n, int c, int64_t hw,
+                                float threshold, float* stats_out, void* workspace, size_t workspace_bytes,
+                                b200ssl_stream_t stream) {
+  using namespace b200ssl;
+  B200SSL_REQUIRE(n >= 1 && c >= 1 && hw >= 1, "consistency_forward: bad extents");
+  B200SSL_REQUIRE(n <= 65535, "consistency_forward: too many images");
+  B200SSL_REQUIRE(student && teacher && stats_out, "consistency_forward: null argument");
+  const int bx = cons_blocks(n, hw);
+  const size_t need = (size_t)n * bx * 2 * sizeof(double);
+  if (!workspace || workspace_bytes < need) {
+    set_error("consistency_forward: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return B200SSL_EWORKSPACE;
+  }
+  const bool vec = aligned16(student) && aligned16(teacher) && (hw % 4 == 0);
+  cudaStream_t s = (cudaStream_t)stream;
+  prof_begin("consistency_partial", s);
+  consistency_partial_kernel<<<dim3((unsigned)bx, (unsigned)n), kConsThreads, 0, s>>>(
+      student, teacher, c, hw, threshold, static_cast<double*>(workspace), vec);
+  int rc = check_launch("consistency partial");
+  if (rc) return rc;
+  prof_begin("consistency_final", s);
+  consistency_final_kernel<<<1, 32, 0, s>>>(static_cast<const double*>(workspace), n * bx, (double)n * (double)hw,
+                                            stats_out);
+  return check_launch("consistency final");
+}
+
+int b200ssl_consistency_backward(const float* student, const float* teacher, int n, int c, int64_t hw,
+                                 float threshold, const float* stats, const float* grad_out,
+                                 float* grad_student, b200ssl_stream_t stream) {
+  using namespace b200ssl;
+  B200SSL_REQUIRE(n >= 1 && c >= 1 && hw >= 1, "consistency_backward: bad extents");
+  B200SSL_REQUIRE(n <= 65535, "consistency_backward: too many images");
+  B200SSL_REQUIRE(student && teacher && stats && grad_out && grad_student, "consistency_backward: null argument");
+  const bool vec = aligned16(student) && aligned16(teacher) && aligned16(grad_student) && (hw % 4 == 0);
+  cudaStream_t s = (cudaStream_t)stream;
+  prof_begin("consistency_grad", s);
+  consistency_grad_kernel<<<dim3((unsigned)cons_blocks(n, hw), (unsigned)n), kConsThreads, 0, s>>>(
+      student, teacher, c, hw, threshold, stats, grad_out, grad_student, vec);
+  return check_launch("consistency grad");
+}
+
+}  // extern "C"

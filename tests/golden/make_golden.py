@@ -214,6 +214,26 @@ def mix_case():
          out_special=ref_cowmix.mix_with_mask(a2, b2, mask).numpy())
 
 
+def consistency_case():
+    """train.py:98-107 is inline code inside train() and train.py does not import here (kornia is not
+    installed), so these vectors come from executing the same ATen op sequence, line for line, as
+    restated in oracle/torch_port.confidence_masked_consistency -- the one golden file that is NOT
+    produced by a reference function."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from oracle import torch_port
+    gen = torch.Generator().manual_seed(53)
+    n, c, h, w = 2, 3, 20, 28
+    student = torch.randn(n, c, h, w, generator=gen) * 3
+    teacher = torch.randn(n, c, h, w, generator=gen) * 3
+    out = dict(student=student.numpy(), teacher=teacher.numpy())
+    for tag, thr in [("t097", 0.97), ("t06", 0.6)]:
+        x = student.clone().requires_grad_(True)
+        loss, conf = torch_port.confidence_masked_consistency(x, teacher, thr)
+        loss.backward()
+        out[f"{tag}_loss"], out[f"{tag}_conf"], out[f"{tag}_grad"] = loss.detach().numpy(), conf.numpy(), x.grad.numpy()
+    save("consistency", **out)
+
+
 if __name__ == "__main__":
     cowmix_case("cowmix_small", 3, 40, 56, (0.4, 0.6), (1.0, 3.0), seed=3)
     cowmix_case("cowmix_c1", 2, 256, 256, (0.45, 0.55), (8, 32), seed=0)      # BASELINE configs[0]
@@ -222,3 +242,4 @@ if __name__ == "__main__":
     ema_case()
     metrics_case()
     mix_case()
+    consistency_case()

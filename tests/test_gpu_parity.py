@@ -549,3 +549,50 @@ def test_loss_path_step_binary_fused_and_fallback_shapes(ssl, dev, n, c, h, w):
     l2 = ssl.losses.binary_lovasz_loss_with_logits(x, target.to(dev))
     l2.backward()
     assert float(l2) == float(out["loss"]) and same_nonzero_bits(x.grad.cpu().numpy(), out["grad"].cpu().numpy())
+
+
+# ================================================================================ consistency loss (N1)
+def _clear_of_threshold(teacher, thr, margin=1e-4):
+    """move teacher logits whose sigmoid is within `margin` of the threshold (confidence flips there
+    depend on the last bit of exp)"""
+    t = torch.sigmoid(teacher)
+    near = (t - thr).abs() < margin
+    return torch.where(near, teacher + 0.05, teacher)
+
+
+def test_consistency_golden(ssl, dev):
+    g = load_golden("consistency")
+    for tag, thr in [("t097", 0.97), ("t06", 0.6)]:
+        x = torch.from_numpy(g["student"]).to(dev).requires_grad_(True)
+        loss, conf = ssl.consistency.confidence_masked_consistency(x, torch.from_numpy(g["teacher"]).to(dev), thr)
+        loss.backward()
+        assert abs(float(loss) - float(g[f"{tag}_loss"])) <= REL * abs(float(g[f"{tag}_loss"]))
+        assert float(conf) == float(g[f"{tag}_conf"])
+        ref = g[f"{tag}_grad"]
+        got = x.grad.cpu().numpy()
+        assert np.linalg.norm(got - ref) <= REL * np.linalg.norm(ref)
+        assert np.array_equal(got == 0, ref == 0)
+
+
+@pytest.mark.parametrize("n,c,h,w,thr", [(2, 2, 64, 64, 0.97), (3, 19, 33, 47, 0.6), (1, 1, 5, 7, 0.5), (16, 2, 512, 512, 0.97)])
+def test_consistency_vs_oracle(ssl, dev, n, c, h, w, thr):
+    gen = torch.Generator().manual_seed(n + c + h)
+    student = torch.randn(n, c, h, w, generator=gen) * 3
+    teacher = _clear_of_threshold(torch.randn(n, c, h, w, generator=gen) * 3, thr)
+    x = student.to(dev).requires_grad_(True)
+    loss, conf = ssl.consistency.confidence_masked_consistency(x, teacher.to(dev), thr)
+    (loss * 10.0).backward()                                   # consistency_loss_weight (train.py:112)
+    o_loss, o_conf, o_grad = oracle.consistency_loss(student.numpy(), teacher.numpy(), thr, grad_out=10.0)
+    assert abs(float(loss) - float(o_loss)) <= REL * abs(float(o_loss))
+    assert abs(float(conf) - float(o_conf)) <= 1e-7
+    got = x.grad.cpu().numpy()
+    assert np.linalg.norm(got - o_grad) <= REL * np.linalg.norm(o_grad)
+    # elementwise: s - t cancels where student and teacher agree, so the bound is absolute (1e-6 of the largest entry)
+    assert np.allclose(got, o_grad, rtol=1e-4, atol=1e-6 * float(np.abs(o_grad).max()))
+
+
+def test_consistency_no_confident_pixel_is_nan_like_the_reference(ssl, dev):
+    student = torch.zeros(1, 2, 8, 8, device=dev)
+    teacher = torch.zeros(1, 2, 8, 8, device=dev)              # sigmoid = 0.5 < 0.97 everywhere
+    loss, conf = ssl.consistency.confidence_masked_consistency(student, teacher, 0.97)
+    assert torch.isnan(loss) and float(conf) == 0.0

@@ -213,3 +213,15 @@ def test_dice():
     d = (np.float32(2) * tp.astype(np.float32) + np.float32(1)) / ((2 * tp + fp + fn).astype(np.float32) + np.float32(1))
     assert np.array_equal(bits(d), bits(g["dice"]))
     assert np.array_equal(bits(torch_port.dice_metric(torch.from_numpy(g["dice_x"]), torch.from_numpy(g["dice_y"])).numpy()), bits(g["dice"]))
+
+
+# ------------------------------------------------------------------------------ consistency (N1)
+def test_consistency_oracle_vs_golden():
+    g = load_golden("consistency")
+    for tag, thr in [("t097", 0.97), ("t06", 0.6)]:
+        loss, conf, grad = oracle.consistency_loss(g["student"], g["teacher"], thr)
+        assert abs(float(loss) - float(g[f"{tag}_loss"])) <= 1e-5 * abs(float(g[f"{tag}_loss"]))
+        assert float(conf) == float(g[f"{tag}_conf"])
+        ref = g[f"{tag}_grad"]
+        assert np.linalg.norm(grad - ref) <= 1e-5 * np.linalg.norm(ref)
+        assert np.array_equal(grad == 0, ref == 0)                 # same confident pixels
