@@ -12,10 +12,13 @@
  *   - all data pointers are DEVICE pointers unless the name ends in `_host`.
  *   - tensors are dense, row-major NCHW fp32 unless stated; labels are int64 by
  *     default (torch.argmax convention), see b200ssl_label_dtype.
- *   - the library allocates nothing, frees nothing, never synchronises and never
- *     touches the legacy default stream: the caller owns every buffer and passes
- *     a workspace (size from the matching *_workspace_bytes query) and a stream
- *     (cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream).
+ *   - the library allocates no device memory, frees nothing, never synchronises and
+ *     never touches the legacy default stream: the caller owns every buffer and
+ *     passes a workspace (size from the matching *_workspace_bytes query) and a
+ *     stream (cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream).  The only
+ *     resources it creates are two internal non-blocking streams and three events
+ *     per device for the fork/join inside b200ssl_loss_path_step, and the CUDA events
+ *     of the optional profiler.
  *   - 16-byte aligned bases take the 128-bit path; other alignments fall back to
  *     scalar accesses inside the same kernel (never an error).
  */
@@ -281,8 +284,11 @@ int b200ssl_consistency_backward(const float* student, const float* teacher, int
 /* ---------------------------------------------------------------------------------------------
  * The whole loss path of one semi-supervised step in one call (train.py:65-130 order): mask, fused
  * mix of images + teacher predictions, Lovasz forward/backward (unit upstream gradient), EMA,
- * confusion matrix of (labels, argmax scores).  Chains the entry points above on `stream`; any stage
- * whose input pointer is NULL (noise / image_a / scores / ema_table / cm) is skipped.
+ * confusion matrix of (labels, argmax scores).  Chains the entry points above; any stage whose input
+ * pointer is NULL (noise / image_a / scores / ema_table / cm) is skipped.  The three independent
+ * chains (mask+mix, Lovasz+matrix, EMA) are forked onto two internal side streams after the work
+ * already queued on `stream` and joined back into it before the call returns, so the caller sees one
+ * stream-ordered operation (set `serial` to keep everything on `stream`).
  *   mode BINARY : losses.binary_lovasz_loss_with_logits (losses.py:239-250); target = soft one-hot
  *                 fp32 [n,C,h,w]; labels_u8 [n,h,w] and nonzero [n] are scratch/outputs
  *   mode SOFTMAX: lovasz.lovasz_softmax with `lovasz` as given; target = integer labels [n,h,w]
@@ -294,7 +300,8 @@ int b200ssl_consistency_backward(const float* student, const float* teacher, int
 typedef struct b200ssl_step_desc {
   int32_t n, classes, h, w, image_channels, K, mode, cm_has_ignore;
   int64_t cm_ignore_index;
-  int32_t cm_label_dtype, reserved_;
+  int32_t cm_label_dtype;
+  int32_t serial; /* != 0: keep every kernel on `stream` (default 0: fork the independent chains) */
   b200ssl_lovasz_desc lovasz;
   /* inputs */
   const float* noise;      /* [n,1,h,w] */

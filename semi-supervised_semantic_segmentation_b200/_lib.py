@@ -44,7 +44,7 @@ class StepDesc(C.Structure):
     """b200ssl_step_desc (include/b200ssl.h)."""
     _fields_ = (
         [(k, C.c_int32) for k in ("n", "classes", "h", "w", "image_channels", "K", "mode", "cm_has_ignore")] +
-        [("cm_ignore_index", C.c_int64), ("cm_label_dtype", C.c_int32), ("reserved_", C.c_int32),
+        [("cm_ignore_index", C.c_int64), ("cm_label_dtype", C.c_int32), ("serial", C.c_int32),
          ("lovasz", LovaszDesc)] +
         [(k, C.c_void_p) for k in ("noise", "taps", "thr_factor", "image_a", "image_b", "teacher_a", "teacher_b",
                                    "scores", "target", "cm_labels", "mask", "mixed_images", "mixed_teacher",

@@ -2,18 +2,53 @@
 //   mask (cowmix.py:56-68) -> fused mix of images and teacher predictions (cowmix.py:72-73 x2)
 //   -> Lovasz forward + backward (lovasz.py / losses.py:239-250) -> EMA (mean_teacher.py:10-11)
 //   -> confusion matrix of (labels, argmax scores).
-// It only chains the per-stage entry points of this library on one stream; the point is host cost:
-// ~20 kernel launches issued back to back from C (~2.5 us each) instead of ~20 Python/ctypes round
-// trips, so a 16x512x512 step stays GPU-bound.
+// It chains the per-stage entry points of this library.  Two things make it faster than calling them
+// one by one:
+//   * host cost: ~15 launches issued back to back from C (~2.5 us each) instead of as many
+//     Python/ctypes round trips, so a 16x512x512 step stays GPU-bound;
+//   * the three chains of the path are independent of each other -- (mask -> mix), (Lovasz +
+//     confusion matrix) and (EMA) -- and bound by different units (fp32 FMA issue, latency/issue of
+//     the radix passes, HBM), so they are forked onto two internal side streams and joined back
+//     into the caller's stream: the caller still sees ONE stream-ordered operation.
+#include <mutex>
+
 #include "common.cuh"
 
-extern "C" int b200ssl_loss_path_step(const b200ssl_step_desc* d, b200ssl_stream_t stream) {
+namespace b200ssl {
+
+struct SideStreams {
+  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+  bool ok = false;
+};
+
+// one set per device, created on first use (non-blocking streams, timing-less events)
+static SideStreams* side_streams() {
+  static std::mutex mu;
+  static SideStreams per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  SideStreams& ss = per_dev[dev];
+  if (!ss.ok) {
+    bool good = cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2 && good; ++i)
+      good = cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ss.join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!good) return nullptr;
+    ss.ok = true;
+  }
+  return &ss;
+}
+
+}  // namespace b200ssl
+
+static int loss_path_step_on(const b200ssl_step_desc* d, b200ssl_stream_t s_mix, b200ssl_stream_t s_lovasz,
+                             b200ssl_stream_t s_ema) {
   using namespace b200ssl;
-  B200SSL_REQUIRE(d != nullptr, "loss_path_step: null descriptor");
-  B200SSL_REQUIRE(d->n >= 1 && d->classes >= 1 && d->h >= 1 && d->w >= 1, "loss_path_step: bad extents");
-  B200SSL_REQUIRE(d->mode == B200SSL_STEP_BINARY || d->mode == B200SSL_STEP_SOFTMAX, "loss_path_step: bad mode");
   const int64_t hw = (int64_t)d->h * d->w;
   int rc;
+  b200ssl_stream_t stream = s_mix;
 
   // 1. mask
   if (d->noise) {
@@ -28,6 +63,7 @@ extern "C" int b200ssl_loss_path_step(const b200ssl_step_desc* d, b200ssl_stream
     if (rc) return rc;
   }
   // 3. Lovasz forward + backward with the upstream gradient small[2], 5. confusion matrix
+  stream = s_lovasz;
   if (d->scores) {
     float* loss = d->small;        // [0] loss  [1] denom  [2] upstream gradient (1.0)
     bool done = false;
@@ -79,9 +115,36 @@ extern "C" int b200ssl_loss_path_step(const b200ssl_step_desc* d, b200ssl_stream
     }
   }
   // 4. EMA over all parameters
+  stream = s_ema;
   if (d->ema_table && d->ema_entries > 0) {
     rc = b200ssl_ema_multi(d->ema_table, d->ema_entries, d->ema_alpha, stream);
     if (rc) return rc;
   }
   return 0;
+}
+
+extern "C" int b200ssl_loss_path_step(const b200ssl_step_desc* d, b200ssl_stream_t stream) {
+  using namespace b200ssl;
+  B200SSL_REQUIRE(d != nullptr, "loss_path_step: null descriptor");
+  B200SSL_REQUIRE(d->n >= 1 && d->classes >= 1 && d->h >= 1 && d->w >= 1, "loss_path_step: bad extents");
+  B200SSL_REQUIRE(d->mode == B200SSL_STEP_BINARY || d->mode == B200SSL_STEP_SOFTMAX, "loss_path_step: bad mode");
+  cudaStream_t main = (cudaStream_t)stream;
+  const bool has_mix = d->noise || d->image_a, has_lov = d->scores != nullptr;
+  const bool has_ema = d->ema_table && d->ema_entries > 0;
+  SideStreams* ss = ((int)has_mix + (int)has_lov + (int)has_ema >= 2 && !d->serial) ? side_streams() : nullptr;
+  if (!ss) return loss_path_step_on(d, stream, stream, stream);
+  // fork: the side streams start after everything already queued on the caller's stream
+  if (cudaEventRecord(ss->fork, main) != cudaSuccess || cudaStreamWaitEvent(ss->s[0], ss->fork, 0) != cudaSuccess ||
+      cudaStreamWaitEvent(ss->s[1], ss->fork, 0) != cudaSuccess) {
+    set_error("loss_path_step: fork failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return (int)cudaErrorUnknown;
+  }
+  // the longest chain (Lovasz) stays on the caller's stream
+  const int rc = loss_path_step_on(d, ss->s[0], stream, ss->s[1]);
+  // join (also on error paths, so that the caller's stream never runs ahead of the side work)
+  for (int i = 0; i < 2; ++i) {
+    cudaEventRecord(ss->join[i], ss->s[i]);
+    cudaStreamWaitEvent(main, ss->join[i], 0);
+  }
+  return rc;
 }

@@ -23,7 +23,7 @@ from . import cowmix, lovasz, mean_teacher
 
 class LossPathStep:
     def __init__(self, num_classes, mask_proportion_range=(0.45, 0.55), sigma_range=(8, 32),
-                 ema_alpha=0.99, mode="binary", classes="present", per_image=False, ignore=255):
+                 ema_alpha=0.99, mode="binary", classes="present", per_image=False, ignore=255, serial=False):
         if mode not in ("binary", "softmax"):
             raise ValueError("mode must be 'binary' (losses.binary_lovasz_loss_with_logits) or 'softmax'")
         self.num_classes = num_classes
@@ -34,6 +34,7 @@ class LossPathStep:
         self.classes = classes
         self.per_image = per_image
         self.ignore = ignore
+        self.serial = serial      # True: keep every kernel on the current stream (no internal fork/join)
         self._ema = mean_teacher.EmaUpdater()
         self._scratch_key = None
         self._scratch = None
@@ -106,6 +107,7 @@ class LossPathStep:
             d = _lib.StepDesc()
             d.n, d.classes, d.h, d.w = n, c, h, w
             d.mode = _lib.STEP_BINARY if binary else _lib.STEP_SOFTMAX
+            d.serial = 1 if self.serial else 0
             d.lovasz = desc_l
             out = {}
             # ---- mask + mix (skipped when no images are given)
