@@ -114,6 +114,25 @@ def main():
     bytes_ = 4 * (3 * 3 + 3 * c + 1) * n * h * w
     out[f"mix2_{n}x{c}x{h}x{w}"] = {"ms": round(ms, 4), "GBps": round(bytes_ / ms / 1e6, 1),
                                     "frac": round(bytes_ / ms / 1e6 / PEAK, 3)}
+    # ---- the whole configs[1] step: this library vs the reference's ATen op sequence on the SAME GPU
+    # (stock ATen/cub/cuDNN kernels; SURVEY 2.2: "the Blackwell kernel to beat").  oracle.torch_port is
+    # test infrastructure; it is imported here only as the thing being compared against.
+    from oracle import torch_port
+    inp = bench.make_inputs(dev, 0)
+    W = bench.WORKLOAD
+    P = W["n"] * W["h"] * W["w"]
+    step = b200ssl.LossPathStep(num_classes=W["c"], mode="binary")
+    ms = timeit(lambda: step(inp["image_a"], inp["image_b"], inp["teacher_a"], inp["teacher_b"], inp["scores"],
+                             inp["target"], inp["params"], inp["ema_params"]), reps=5, inner=20)
+    ema_ref = [e.clone() for e in inp["ema_params"]]
+
+    def aten_step():
+        torch_port.loss_path_step(inp["image_a"], inp["image_b"], inp["teacher_a"], inp["teacher_b"], inp["scores"],
+                                  inp["target"], inp["params"], ema_ref, mode="binary", num_classes=W["c"])
+    ms_ref = timeit(aten_step, reps=3, warm=2, inner=2)
+    out["step_configs1_16x512x512"] = {"b200ssl_ms": round(ms, 4), "b200ssl_Mpix_s": round(P / ms / 1e3, 1),
+                                       "aten_cuda_ms": round(ms_ref, 3), "aten_cuda_Mpix_s": round(P / ms_ref / 1e3, 1),
+                                       "speedup_vs_aten_cuda": round(ms_ref / ms, 1)}
     print(json.dumps(out))
 
 

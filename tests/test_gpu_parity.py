@@ -596,3 +596,32 @@ def test_consistency_no_confident_pixel_is_nan_like_the_reference(ssl, dev):
     teacher = torch.zeros(1, 2, 8, 8, device=dev)              # sigmoid = 0.5 < 0.97 everywhere
     loss, conf = ssl.consistency.confidence_masked_consistency(student, teacher, 0.97)
     assert torch.isnan(loss) and float(conf) == 0.0
+
+
+def test_loss_path_step_forked_equals_serial(ssl, dev):
+    """The internal fork/join of the three chains must not change a single bit, and work queued on the
+    caller's stream right after the call must see all results."""
+    gen = torch.Generator().manual_seed(5)
+    n, c, h, w = 4, 2, 128, 128
+    d = lambda t: t.to(dev)
+    ia, ib = d(torch.rand(n, 3, h, w, generator=gen)), d(torch.rand(n, 3, h, w, generator=gen))
+    ta, tb = d(torch.randn(n, c, h, w, generator=gen)), d(torch.randn(n, c, h, w, generator=gen))
+    logits = d(torch.randn(n, c, h, w, generator=gen) * 3)
+    lab = coherent_labels(gen, n, c, h, w)
+    target = d(torch.nn.functional.one_hot(lab, c).permute(0, 3, 1, 2).float().contiguous())
+    params = [d(torch.randn(s, generator=gen)) for s in [(300, 7), (9000,), (3,)]]
+    outs = []
+    for serial in (True, False, False):
+        ema = [p.clone() * 0.5 for p in params]
+        torch.manual_seed(123)
+        step = ssl.LossPathStep(num_classes=c, sigma_range=(2, 6), serial=serial)
+        o = step(ia, ib, ta, tb, logits, target, params, ema)
+        # consumers on the caller's stream, queued immediately
+        summary = torch.stack([o["mask"].sum(), o["mixed_images"].sum(), o["mixed_teacher"].sum(),
+                               o["grad"].abs().sum(), o["loss"], o["cm"].sum().float(), sum(e.sum() for e in ema)])
+        outs.append((o, ema, summary))
+    for o, ema, summary in outs[1:]:
+        assert torch.equal(summary, outs[0][2])
+        for k in ("mask", "mixed_images", "mixed_teacher", "grad", "cm", "labels"):
+            assert torch.equal(o[k], outs[0][0][k]), k
+        assert all(torch.equal(a, b) for a, b in zip(ema, outs[0][1]))
