@@ -145,6 +145,7 @@ def algorithmic_bytes(P, C, n_params, label_bytes=1):
     return {
         "cowmix_conv_pass1": 8 * P, "cowmix_conv_pass2": 8 * P, "cowmix_threshold": 8 * P,
         "mix2": 4 * (3 * 3 + 3 * C + 1) * P,
+        "mix2_threshold": 4 * (3 * 3 + 3 * C + 2) * P,
         "argmax_channels": (4 * C + label_bytes) * P,
         "lovasz_keybuild": (4 + label_bytes + 8) * P,
         "lovasz_binary_prep": (8 * C + label_bytes + 8) * P,

@@ -122,6 +122,17 @@ int b200ssl_cowmix_mask(const float* noise, const float* taps, int K, const floa
                         int n, int h, int w, float* mask_out, float* field_out, void* workspace,
                         size_t workspace_bytes, b200ssl_stream_t stream);
 
+/* The same pipeline split for fusion: b200ssl_cowmix_field stops after the smoothing and the
+ * per-sample threshold (field_out = S [n,h,w], tau_out [n]); b200ssl_mix2_field forms the mask
+ * S > tau[image] on the fly while mixing and writes it to mask_out -- bit-identical to
+ * b200ssl_cowmix_mask followed by b200ssl_mix2, one pass over S and one launch fewer. */
+int b200ssl_cowmix_field(const float* noise, const float* taps, int K, const float* thr_factor, int n, int h,
+                         int w, float* field_out, float* tau_out, void* workspace, size_t workspace_bytes,
+                         b200ssl_stream_t stream);
+int b200ssl_mix2_field(const float* a0, const float* b0, float* out0, int c0, const float* a1,
+                       const float* b1, float* out1, int c1, const float* field, const float* tau,
+                       float* mask_out, int64_t n, int64_t hw, b200ssl_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Lovasz-softmax forward (+ unit gradients) and backward.
  * Replaces lovasz.lovasz_softmax / lovasz_softmax_flat / flatten_probas / lovasz_grad,

@@ -68,6 +68,8 @@ SIGNATURES = {
     "b200ssl_mix2": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i64, _i64, _vp]),
     "b200ssl_cowmix_workspace_bytes": (_sz, [_i, _i, _i]),
     "b200ssl_cowmix_mask": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "b200ssl_cowmix_field": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "b200ssl_mix2_field": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i64, _i64, _vp]),
     "b200ssl_lovasz_num_segments": (C.c_int32, [C.POINTER(LovaszDesc)]),
     "b200ssl_lovasz_workspace_bytes": (_sz, [C.POINTER(LovaszDesc)]),
     "b200ssl_lovasz_forward": (_i, [C.POINTER(LovaszDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -326,6 +326,35 @@ conv_slow_axis_transposed(const float* __restrict__ in, float* __restrict__ out,
   }
 }
 
+// tau_n = RN(RN(factor_n * std_n) + mean_n) from the per-block partial sums (cowmix.py:60-66);
+// call with the first warp of a block, the result is valid in lane 0
+__device__ __forceinline__ float cowmix_tau_from_partials(const double* __restrict__ partials,
+                                                          int partials_per_sample, int n, long long plane,
+                                                          float factor) {
+  // fixed-order reduction of the per-block partial sums (deterministic)
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < partials_per_sample; i += 32) {
+    s1 += partials[((long long)n * partials_per_sample + i) * 2 + 0];
+    s2 += partials[((long long)n * partials_per_sample + i) * 2 + 1];
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  const double M = (double)plane;
+  const double mean = s1 / M;
+  double var = (s2 - s1 * s1 / M) / (M - 1.0);  // unbiased; a 1-pixel plane gives NaN like torch
+  if (var < 0.0) var = 0.0;
+  const float stdf = (float)sqrt(var);
+  return __fadd_rn(__fmul_rn(factor, stdf), (float)mean);
+}
+
+// one warp per sample: tau[n] for the fused threshold+mix kernel
+__global__ void cowmix_tau_kernel(const float* __restrict__ thr_factor, const double* __restrict__ partials,
+                                  int partials_per_sample, long long plane, float* __restrict__ tau) {
+  const int n = blockIdx.x;
+  const float t = cowmix_tau_from_partials(partials, partials_per_sample, n, plane, thr_factor[n]);
+  if (threadIdx.x == 0) tau[n] = t;
+}
+
 // mask = (S > tau_n) with tau_n = RN(RN(factor_n * std_n) + mean_n)   (cowmix.py:60-68)
 __global__ void __launch_bounds__(256)
 cowmix_threshold_kernel(const float* __restrict__ S, const float* __restrict__ thr_factor,
@@ -334,22 +363,8 @@ cowmix_threshold_kernel(const float* __restrict__ S, const float* __restrict__ t
   __shared__ float tau_s;
   const int n = blockIdx.y;
   if (threadIdx.x < 32) {
-    // fixed-order reduction of the per-block partial sums (deterministic)
-    double s1 = 0.0, s2 = 0.0;
-    for (int i = threadIdx.x; i < partials_per_sample; i += 32) {
-      s1 += partials[((long long)n * partials_per_sample + i) * 2 + 0];
-      s2 += partials[((long long)n * partials_per_sample + i) * 2 + 1];
-    }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (threadIdx.x == 0) {
-      const double M = (double)plane;
-      const double mean = s1 / M;
-      double var = (s2 - s1 * s1 / M) / (M - 1.0);  // unbiased; a 1-pixel plane gives NaN like torch
-      if (var < 0.0) var = 0.0;
-      const float stdf = (float)sqrt(var);
-      tau_s = __fadd_rn(__fmul_rn(thr_factor[n], stdf), (float)mean);
-    }
+    const float t = cowmix_tau_from_partials(partials, partials_per_sample, n, plane, thr_factor[n]);
+    if (threadIdx.x == 0) tau_s = t;
   }
   __syncthreads();
   const float tau = tau_s;
@@ -465,21 +480,20 @@ size_t b200ssl_cowmix_workspace_bytes(int n, int h, int w) {
   bytes += align_up((size_t)n * plane * sizeof(float), 256);  // Vt
   bytes += align_up((size_t)n * plane * sizeof(float), 256);  // S (when field_out is NULL)
   bytes += align_up((size_t)n * pps * 2 * sizeof(double), 256);
+  bytes += align_up((size_t)n * sizeof(float), 256);          // tau scratch (fused threshold+mix in the step)
   return bytes;
 }
 
-int b200ssl_cowmix_mask(const float* noise, const float* taps, int K, const float* thr_factor,
-                        int n, int h, int w, float* mask_out, float* field_out, void* workspace,
-                        size_t workspace_bytes, b200ssl_stream_t stream) {
+// conv passes: noise -> S (+ per-block statistics); shared by b200ssl_cowmix_mask / _field
+static int cowmix_field_impl(const float* noise, const float* taps, int K, int n, int h, int w, float* field_out,
+                             void* workspace, size_t workspace_bytes, cudaStream_t s, const char* who,
+                             float** S_out, double** partials_out, int* pps_out, float** tau_ws_out) {
   using namespace b200ssl;
-  B200SSL_REQUIRE(n >= 0 && h >= 0 && w >= 0, "cowmix_mask: negative extent");
-  if (n == 0 || h == 0 || w == 0) return 0;
-  B200SSL_REQUIRE(n <= 65535, "cowmix_mask: batch too large");
-  B200SSL_REQUIRE(K >= 1 && (K & 1) == 1, "cowmix_mask: K must be odd and >= 1 (got %d)", K);
-  B200SSL_REQUIRE(noise && taps && thr_factor && mask_out, "cowmix_mask: null argument");
+  B200SSL_REQUIRE(n <= 65535, "%s: batch too large", who);
+  B200SSL_REQUIRE(K >= 1 && (K & 1) == 1, "%s: K must be odd and >= 1 (got %d)", who, K);
   const size_t need = b200ssl_cowmix_workspace_bytes(n, h, w);
   if (!workspace || workspace_bytes < need) {
-    set_error("cowmix_mask: workspace too small (%zu < %zu)", workspace_bytes, need);
+    set_error("%s: workspace too small (%zu < %zu)", who, workspace_bytes, need);
     return B200SSL_EWORKSPACE;
   }
   const size_t plane = (size_t)h * w;
@@ -489,11 +503,12 @@ int b200ssl_cowmix_mask(const float* noise, const float* taps, int K, const floa
   float* S = field_out ? field_out : reinterpret_cast<float*>(ws);
   ws += align_up((size_t)n * plane * sizeof(float), 256);
   double* partials = reinterpret_cast<double*>(ws);
+  const int pps_max = max(conv_grid(n, w, h).partials_per_sample, conv_tma_grid(n, w, h).partials_per_sample);
+  ws += align_up((size_t)n * pps_max * 2 * sizeof(double), 256);
+  *tau_ws_out = reinterpret_cast<float*>(ws);
 
-  cudaStream_t s = (cudaStream_t)stream;
   const size_t smem = (size_t)(K + 3 * kConvR) * sizeof(float2);
-  B200SSL_REQUIRE(smem <= 48 * 1024, "cowmix_mask: K=%d too large", K);
-  B200SSL_REQUIRE(n <= 65535, "cowmix_mask: too many samples");
+  B200SSL_REQUIRE(smem <= 48 * 1024, "%s: K=%d too large", who, K);
 
   // pass 1: along H (slow axis of noise[n][H][W]) -> Vt[n][W][H]
   if (conv_tma_ok(noise, K, h, w)) {
@@ -526,6 +541,47 @@ int b200ssl_cowmix_mask(const float* noise, const float* taps, int K, const floa
     int rc = check_launch("cowmix conv pass 2");
     if (rc) return rc;
   }
+  *S_out = S;
+  *partials_out = partials;
+  *pps_out = g2.partials_per_sample;
+  return 0;
+}
+
+int b200ssl_cowmix_field(const float* noise, const float* taps, int K, const float* thr_factor, int n, int h,
+                         int w, float* field_out, float* tau_out, void* workspace, size_t workspace_bytes,
+                         b200ssl_stream_t stream) {
+  using namespace b200ssl;
+  B200SSL_REQUIRE(n >= 0 && h >= 0 && w >= 0, "cowmix_field: negative extent");
+  if (n == 0 || h == 0 || w == 0) return 0;
+  B200SSL_REQUIRE(noise && taps && thr_factor && field_out && tau_out, "cowmix_field: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  float *S, *tau_ws;
+  double* partials;
+  int pps;
+  int rc = cowmix_field_impl(noise, taps, K, n, h, w, field_out, workspace, workspace_bytes, s, "cowmix_field", &S,
+                             &partials, &pps, &tau_ws);
+  if (rc) return rc;
+  prof_begin("cowmix_tau", s);
+  cowmix_tau_kernel<<<n, 32, 0, s>>>(thr_factor, partials, pps, (long long)h * w, tau_out);
+  return check_launch("cowmix tau");
+}
+
+int b200ssl_cowmix_mask(const float* noise, const float* taps, int K, const float* thr_factor,
+                        int n, int h, int w, float* mask_out, float* field_out, void* workspace,
+                        size_t workspace_bytes, b200ssl_stream_t stream) {
+  using namespace b200ssl;
+  B200SSL_REQUIRE(n >= 0 && h >= 0 && w >= 0, "cowmix_mask: negative extent");
+  if (n == 0 || h == 0 || w == 0) return 0;
+  B200SSL_REQUIRE(K >= 1 && (K & 1) == 1, "cowmix_mask: K must be odd and >= 1 (got %d)", K);
+  B200SSL_REQUIRE(noise && taps && thr_factor && mask_out, "cowmix_mask: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t plane = (size_t)h * w;
+  float *S, *tau_ws;
+  double* partials;
+  int pps;
+  int rc = cowmix_field_impl(noise, taps, K, n, h, w, field_out, workspace, workspace_bytes, s, "cowmix_mask", &S,
+                             &partials, &pps, &tau_ws);
+  if (rc) return rc;
   {
     const bool vec = (plane % 4 == 0) && aligned16(S) && aligned16(mask_out);
     long long bx = (long long)((vec ? plane / 4 : plane) + 255) / 256;
@@ -535,7 +591,7 @@ int b200ssl_cowmix_mask(const float* noise, const float* taps, int K, const floa
     if (bx < 1) bx = 1;
     prof_begin("cowmix_threshold", s);
     cowmix_threshold_kernel<<<dim3((unsigned)bx, (unsigned)n), 256, 0, s>>>(
-        S, thr_factor, partials, g2.partials_per_sample, (long long)plane, mask_out, vec);
+        S, thr_factor, partials, pps, (long long)plane, mask_out, vec);
     return check_launch("cowmix threshold");
   }
 }

@@ -68,12 +68,14 @@ __device__ __forceinline__ void mix_tensor(const float* __restrict__ a, const fl
   }
 }
 
-template <int VEC, bool CHANNEL_MASK>
+// FIELD: `mask` is the smoothed field S and the {0,1} mask is formed on the fly as S > tau[image]
+// (cowmix.py:68) and written to mask_out -- the threshold pass fused into the mix.
+template <int VEC, bool CHANNEL_MASK, bool FIELD>
 __global__ void __launch_bounds__(kMixThreads, 4)
 mix2_kernel(const float* __restrict__ a0, const float* __restrict__ b0, float* __restrict__ out0,
             int c0, const float* __restrict__ a1, const float* __restrict__ b1,
             float* __restrict__ out1, int c1, const float* __restrict__ mask, long long n,
-            long long hw) {
+            long long hw, const float* __restrict__ tau, float* __restrict__ mask_out) {
   const long long per_img = hw / VEC;
   const long long total = n * per_img;
   for (long long q = (long long)blockIdx.x * kMixThreads + threadIdx.x; q < total;
@@ -83,6 +85,12 @@ mix2_kernel(const float* __restrict__ a0, const float* __restrict__ b0, float* _
     Pack<VEC> m, om;
     if (!CHANNEL_MASK) {
       m.load(mask + n_idx * hw + off);
+      if (FIELD) {
+        const float t = __ldg(tau + n_idx);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) m.at(e) = m.at(e) > t ? 1.0f : 0.0f;
+        m.store(mask_out + n_idx * hw + off);
+      }
 #pragma unroll
       for (int e = 0; e < VEC; ++e) om.at(e) = __fsub_rn(1.0f, m.at(e));
     }
@@ -93,34 +101,51 @@ mix2_kernel(const float* __restrict__ a0, const float* __restrict__ b0, float* _
 
 }  // namespace b200ssl
 
-extern "C" int b200ssl_mix2(const float* a0, const float* b0, float* out0, int c0, const float* a1,
-                            const float* b1, float* out1, int c1, const float* mask,
-                            int mask_channels, int64_t n, int64_t hw, b200ssl_stream_t stream) {
+static int mix2_launch(const float* a0, const float* b0, float* out0, int c0, const float* a1, const float* b1,
+                       float* out1, int c1, const float* mask, int mask_channels, int64_t n, int64_t hw,
+                       const float* tau, float* mask_out, b200ssl_stream_t stream, const char* who) {
   using namespace b200ssl;
-  B200SSL_REQUIRE(n >= 0 && hw >= 0 && c0 >= 0 && c1 >= 0, "mix2: negative extent");
-  if (n == 0 || hw == 0 || (c0 == 0 && c1 == 0)) return 0;
-  B200SSL_REQUIRE(mask != nullptr, "mix2: null mask");
-  B200SSL_REQUIRE(c0 == 0 || (a0 && b0 && out0), "mix2: null tensor 0");
-  B200SSL_REQUIRE(c1 == 0 || (a1 && b1 && out1), "mix2: null tensor 1");
+  B200SSL_REQUIRE(n >= 0 && hw >= 0 && c0 >= 0 && c1 >= 0, "%s: negative extent", who);
+  if (n == 0 || hw == 0 || (c0 == 0 && c1 == 0 && !tau)) return 0;
+  B200SSL_REQUIRE(mask != nullptr, "%s: null mask", who);
+  B200SSL_REQUIRE(c0 == 0 || (a0 && b0 && out0), "%s: null tensor 0", who);
+  B200SSL_REQUIRE(c1 == 0 || (a1 && b1 && out1), "%s: null tensor 1", who);
   const bool chan_mask = (mask_channels != 1);
-  B200SSL_REQUIRE(!chan_mask || (mask_channels == c0 && c1 == 0),
-                  "mix2: per-channel mask needs mask_channels == c0 and no second tensor");
+  B200SSL_REQUIRE(!chan_mask || (mask_channels == c0 && c1 == 0 && !tau),
+                  "%s: per-channel mask needs mask_channels == c0 and no second tensor", who);
   bool vec = (hw % 4 == 0) && aligned16(mask);
   if (c0) vec = vec && aligned16(a0) && aligned16(b0) && aligned16(out0);
   if (c1) vec = vec && aligned16(a1) && aligned16(b1) && aligned16(out1);
+  if (tau) vec = vec && aligned16(mask_out);
   const long long work = (long long)n * (vec ? hw / 4 : hw);
   long long blocks = (work + kMixThreads - 1) / kMixThreads;
   const long long cap = (long long)kNumSMs * 8 * 16;  // grid-stride beyond 16 waves of 8 CTAs/SM
   if (blocks > cap) blocks = cap;
   cudaStream_t s = (cudaStream_t)stream;
-#define LAUNCH(V, CM) \
-  mix2_kernel<V, CM><<<(int)blocks, kMixThreads, 0, s>>>(a0, b0, out0, c0, a1, b1, out1, c1, mask, n, hw)
-  prof_begin("mix2", s);
-  if (vec) {
-    if (chan_mask) LAUNCH(4, true); else LAUNCH(4, false);
+#define LAUNCH(V, CM, F) \
+  mix2_kernel<V, CM, F><<<(int)blocks, kMixThreads, 0, s>>>(a0, b0, out0, c0, a1, b1, out1, c1, mask, n, hw, tau, mask_out)
+  prof_begin(tau ? "mix2_threshold" : "mix2", s);
+  if (tau) {
+    if (vec) LAUNCH(4, false, true); else LAUNCH(1, false, true);
+  } else if (vec) {
+    if (chan_mask) LAUNCH(4, true, false); else LAUNCH(4, false, false);
   } else {
-    if (chan_mask) LAUNCH(1, true); else LAUNCH(1, false);
+    if (chan_mask) LAUNCH(1, true, false); else LAUNCH(1, false, false);
   }
 #undef LAUNCH
-  return check_launch("mix2");
+  return check_launch(who);
+}
+
+extern "C" int b200ssl_mix2(const float* a0, const float* b0, float* out0, int c0, const float* a1,
+                            const float* b1, float* out1, int c1, const float* mask,
+                            int mask_channels, int64_t n, int64_t hw, b200ssl_stream_t stream) {
+  return mix2_launch(a0, b0, out0, c0, a1, b1, out1, c1, mask, mask_channels, n, hw, nullptr, nullptr, stream, "mix2");
+}
+
+extern "C" int b200ssl_mix2_field(const float* a0, const float* b0, float* out0, int c0, const float* a1,
+                                  const float* b1, float* out1, int c1, const float* field, const float* tau,
+                                  float* mask_out, int64_t n, int64_t hw, b200ssl_stream_t stream) {
+  using namespace b200ssl;
+  B200SSL_REQUIRE(tau != nullptr && mask_out != nullptr, "mix2_field: null tau / mask_out");
+  return mix2_launch(a0, b0, out0, c0, a1, b1, out1, c1, field, 1, n, hw, tau, mask_out, stream, "mix2_field");
 }

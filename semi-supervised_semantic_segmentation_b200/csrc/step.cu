@@ -31,9 +31,13 @@ static SideStreams* side_streams() {
   std::lock_guard<std::mutex> lk(mu);
   SideStreams& ss = per_dev[dev];
   if (!ss.ok) {
+    // s[0] carries the Lovasz chain, the longest one: it gets the highest stream priority so that its
+    // blocks are dispatched first and the other chains fill the SMs it leaves free
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     bool good = cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2 && good; ++i)
-      good = cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking) == cudaSuccess &&
+      good = cudaStreamCreateWithPriority(&ss.s[i], cudaStreamNonBlocking, i == 0 ? prio_hi : prio_lo) == cudaSuccess &&
              cudaEventCreateWithFlags(&ss.join[i], cudaEventDisableTiming) == cudaSuccess;
     if (!good) return nullptr;
     ss.ok = true;
@@ -50,17 +54,31 @@ static int loss_path_step_on(const b200ssl_step_desc* d, b200ssl_stream_t s_mix,
   int rc;
   b200ssl_stream_t stream = s_mix;
 
-  // 1. mask
-  if (d->noise) {
-    rc = b200ssl_cowmix_mask(d->noise, d->taps, d->K, d->thr_factor, d->n, d->h, d->w, d->mask, nullptr,
-                             d->ws_cowmix, d->ws_cowmix_bytes, stream);
+  // 1.+2. mask and mix.  With images present the threshold pass is fused into the mix: the field S
+  // and tau live in the cowmix workspace (S in its second region, tau behind the partials).
+  if (d->noise && d->image_a) {
+    const size_t plane_bytes = align_up((size_t)d->n * hw * sizeof(float), 256);
+    float* field = reinterpret_cast<float*>(static_cast<char*>(d->ws_cowmix) + plane_bytes);
+    const size_t need = b200ssl_cowmix_workspace_bytes(d->n, d->h, d->w);
+    B200SSL_REQUIRE(d->ws_cowmix && d->ws_cowmix_bytes >= need, "loss_path_step: cowmix workspace too small");
+    float* tau = reinterpret_cast<float*>(static_cast<char*>(d->ws_cowmix) + need - align_up((size_t)d->n * sizeof(float), 256));
+    rc = b200ssl_cowmix_field(d->noise, d->taps, d->K, d->thr_factor, d->n, d->h, d->w, field, tau, d->ws_cowmix,
+                              d->ws_cowmix_bytes, stream);
     if (rc) return rc;
-  }
-  // 2. mix images (+ teacher predictions) with the same mask
-  if (d->image_a) {
-    rc = b200ssl_mix2(d->image_a, d->image_b, d->mixed_images, d->image_channels, d->teacher_a, d->teacher_b,
-                      d->mixed_teacher, d->teacher_a ? d->classes : 0, d->mask, 1, d->n, hw, stream);
+    rc = b200ssl_mix2_field(d->image_a, d->image_b, d->mixed_images, d->image_channels, d->teacher_a, d->teacher_b,
+                            d->mixed_teacher, d->teacher_a ? d->classes : 0, field, tau, d->mask, d->n, hw, stream);
     if (rc) return rc;
+  } else {
+    if (d->noise) {
+      rc = b200ssl_cowmix_mask(d->noise, d->taps, d->K, d->thr_factor, d->n, d->h, d->w, d->mask, nullptr,
+                               d->ws_cowmix, d->ws_cowmix_bytes, stream);
+      if (rc) return rc;
+    }
+    if (d->image_a) {
+      rc = b200ssl_mix2(d->image_a, d->image_b, d->mixed_images, d->image_channels, d->teacher_a, d->teacher_b,
+                        d->mixed_teacher, d->teacher_a ? d->classes : 0, d->mask, 1, d->n, hw, stream);
+      if (rc) return rc;
+    }
   }
   // 3. Lovasz forward + backward with the upstream gradient small[2], 5. confusion matrix
   stream = s_lovasz;
@@ -139,8 +157,8 @@ extern "C" int b200ssl_loss_path_step(const b200ssl_step_desc* d, b200ssl_stream
     set_error("loss_path_step: fork failed: %s", cudaGetErrorString(cudaGetLastError()));
     return (int)cudaErrorUnknown;
   }
-  // the longest chain (Lovasz) stays on the caller's stream
-  const int rc = loss_path_step_on(d, ss->s[0], stream, ss->s[1]);
+  // Lovasz chain on the high-priority side stream, mask+mix on the caller's stream, EMA on the other
+  const int rc = loss_path_step_on(d, stream, ss->s[0], ss->s[1]);
   // join (also on error paths, so that the caller's stream never runs ahead of the side work)
   for (int i = 0; i < 2; ++i) {
     cudaEventRecord(ss->join[i], ss->s[i]);
