@@ -174,6 +174,7 @@ def run_b200(args, rank, world, local_rank):
     n_params = sum(p.numel() for p in inp["params"])
     step = b200ssl.LossPathStep(num_classes=W["c"], mask_proportion_range=W["p_range"],
                                 sigma_range=W["sigma_range"], ema_alpha=W["alpha"], mode="binary")
+    step.bind_parameters(inp["params"], inp["ema_params"])     # like constructing an optimizer over the lists
     reducer = b200ssl.utils.StepReducer(W["c"], 1, device)
     torch.manual_seed(0)            # the reference seeds every rank with 0 (distributed_trainer.py:17)
 

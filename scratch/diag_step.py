@@ -5,7 +5,7 @@ from b200ssl import _lib
 dev = torch.device('cuda:0')
 inp = bench.make_inputs(dev, 0)
 W = bench.WORKLOAD
-step = b200ssl.LossPathStep(num_classes=2, mode="binary")
+step = b200ssl.LossPathStep(num_classes=2, mode="binary"); step.bind_parameters(inp["params"], inp["ema_params"])
 def one():
     return step(inp["image_a"], inp["image_b"], inp["teacher_a"], inp["teacher_b"], inp["scores"], inp["target"], inp["params"], inp["ema_params"])
 for _ in range(5): one()
