@@ -205,9 +205,10 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- timed region: K steps, device-resident inputs ----
     # The K-step region is timed REPEATS times back to back and the median region is reported (all
-    # of them are listed in "ms_per_step_runs"): one region lasts only ~40 ms, and a single host-side
-    # hiccup on the shared box (seen as 0.42 / 0.42 / 0.88 ms per step in three identical runs)
-    # otherwise decides the number.
+    # of them are listed in "ms_per_step_runs"): one region lasts only ~30 ms, and the first region
+    # after the warm-up regularly contains ONE host-side stall of 4-300 ms inside torch.empty_like
+    # (the caching allocator re-establishing its pool after the synchronisation; found with
+    # B200SSL_BENCH_DEBUG=1), which otherwise decides the number.
     clocks.mark()
     region_ms = []
     launches = 0
@@ -216,9 +217,16 @@ def run_b200(args, rank, world, local_rank):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync_all()
         e0.record()
-        for _ in range(args.steps):
+        t_host = []
+        for _i in range(args.steps):
+            t_a = time.perf_counter()
             out = one_step()
+            t_host.append(time.perf_counter() - t_a)
         e1.record()
+        if os.environ.get("B200SSL_BENCH_DEBUG"):
+            worst = max(t_host)
+            print(f"[debug] region {_rep}: worst host step {worst * 1e3:.2f} ms at {t_host.index(worst)}, "
+                  f"host sum {sum(t_host) * 1e3:.1f} ms", file=sys.stderr)
         sync_all()
         launches = _lib.launch_count() - l0
         t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)

@@ -299,7 +299,7 @@ int b200ssl_consistency_backward(const float* student, const float* teacher, int
  * pointer is NULL (noise / image_a / scores / ema_table / cm) is skipped.  The three independent
  * chains (mask+mix, Lovasz+matrix, EMA) are forked onto two internal side streams after the work
  * already queued on `stream` and joined back into it before the call returns, so the caller sees one
- * stream-ordered operation (set `serial` to keep everything on `stream`).
+ * stream-ordered operation (flag B200SSL_STEP_SERIAL keeps everything on `stream`).
  *   mode BINARY : losses.binary_lovasz_loss_with_logits (losses.py:239-250); target = soft one-hot
  *                 fp32 [n,C,h,w]; labels_u8 [n,h,w] and nonzero [n] are scratch/outputs
  *   mode SOFTMAX: lovasz.lovasz_softmax with `lovasz` as given; target = integer labels [n,h,w]
@@ -307,12 +307,14 @@ int b200ssl_consistency_backward(const float* student, const float* teacher, int
  * --------------------------------------------------------------------------------------------- */
 #define B200SSL_STEP_BINARY 0
 #define B200SSL_STEP_SOFTMAX 1
+#define B200SSL_STEP_SERIAL 1    /* flags: keep every kernel on `stream` (no internal fork/join) */
+#define B200SSL_STEP_PREFORKED 2 /* flags: the fork point was already recorded by b200ssl_loss_path_fork */
 
 typedef struct b200ssl_step_desc {
   int32_t n, classes, h, w, image_channels, K, mode, cm_has_ignore;
   int64_t cm_ignore_index;
   int32_t cm_label_dtype;
-  int32_t serial; /* != 0: keep every kernel on `stream` (default 0: fork the independent chains) */
+  int32_t flags;  /* B200SSL_STEP_SERIAL | B200SSL_STEP_PREFORKED */
   b200ssl_lovasz_desc lovasz;
   /* inputs */
   const float* noise;      /* [n,1,h,w] */
@@ -349,6 +351,15 @@ typedef struct b200ssl_step_desc {
 } b200ssl_step_desc;
 
 int b200ssl_loss_path_step(const b200ssl_step_desc* d, b200ssl_stream_t stream);
+
+/* Optional early fork point.  The Lovasz and EMA chains depend neither on the mask parameters nor on
+ * the noise field, so a caller that produces the noise on `stream` right before the step (torch.normal)
+ * can record the fork point BEFORE doing so: call b200ssl_loss_path_fork(stream), enqueue the noise
+ * generation, then call b200ssl_loss_path_step with B200SSL_STEP_PREFORKED.  The side chains then start
+ * at the recorded point and overlap the noise generation.  Everything the Lovasz / confusion-matrix /
+ * EMA stages read or write (scores, target, grad, labels, cm, small, parameters) must have been
+ * allocated and initialised on `stream` before the fork point. */
+int b200ssl_loss_path_fork(b200ssl_stream_t stream);
 
 /* sizeof() of the ABI structs as compiled into the library, for binding self-checks:
  * which = 0: b200ssl_ema_chunk, 1: b200ssl_lovasz_desc, 2: b200ssl_step_desc; else 0. */

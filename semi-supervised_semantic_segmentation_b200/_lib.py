@@ -38,13 +38,14 @@ class EmaChunk(C.Structure):
 _vp, _i, _i64, _sz, _d = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
 
 STEP_BINARY, STEP_SOFTMAX = 0, 1
+STEP_SERIAL, STEP_PREFORKED = 1, 2
 
 
 class StepDesc(C.Structure):
     """b200ssl_step_desc (include/b200ssl.h)."""
     _fields_ = (
         [(k, C.c_int32) for k in ("n", "classes", "h", "w", "image_channels", "K", "mode", "cm_has_ignore")] +
-        [("cm_ignore_index", C.c_int64), ("cm_label_dtype", C.c_int32), ("serial", C.c_int32),
+        [("cm_ignore_index", C.c_int64), ("cm_label_dtype", C.c_int32), ("flags", C.c_int32),
          ("lovasz", LovaszDesc)] +
         [(k, C.c_void_p) for k in ("noise", "taps", "thr_factor", "image_a", "image_b", "teacher_a", "teacher_b",
                                    "scores", "target", "cm_labels", "mask", "mixed_images", "mixed_teacher",
@@ -89,6 +90,7 @@ SIGNATURES = {
     "b200ssl_consistency_forward": (_i, [_vp, _vp, _i, _i, _i64, C.c_float, _vp, _vp, _sz, _vp]),
     "b200ssl_consistency_backward": (_i, [_vp, _vp, _i, _i, _i64, C.c_float, _vp, _vp, _vp, _vp]),
     "b200ssl_loss_path_step": (_i, [C.POINTER(StepDesc), _vp]),
+    "b200ssl_loss_path_fork": (_i, [_vp]),
     "b200ssl_sizeof": (_sz, [_i]),
 }
 

@@ -149,10 +149,13 @@ extern "C" int b200ssl_loss_path_step(const b200ssl_step_desc* d, b200ssl_stream
   cudaStream_t main = (cudaStream_t)stream;
   const bool has_mix = d->noise || d->image_a, has_lov = d->scores != nullptr;
   const bool has_ema = d->ema_table && d->ema_entries > 0;
-  SideStreams* ss = ((int)has_mix + (int)has_lov + (int)has_ema >= 2 && !d->serial) ? side_streams() : nullptr;
+  const bool serial = (d->flags & B200SSL_STEP_SERIAL) != 0, preforked = (d->flags & B200SSL_STEP_PREFORKED) != 0;
+  SideStreams* ss = ((int)has_mix + (int)has_lov + (int)has_ema >= 2 && !serial) ? side_streams() : nullptr;
   if (!ss) return loss_path_step_on(d, stream, stream, stream);
-  // fork: the side streams start after everything already queued on the caller's stream
-  if (cudaEventRecord(ss->fork, main) != cudaSuccess || cudaStreamWaitEvent(ss->s[0], ss->fork, 0) != cudaSuccess ||
+  // fork: the side streams start after everything already queued on the caller's stream (or at the
+  // point recorded earlier by b200ssl_loss_path_fork)
+  if ((!preforked && cudaEventRecord(ss->fork, main) != cudaSuccess) ||
+      cudaStreamWaitEvent(ss->s[0], ss->fork, 0) != cudaSuccess ||
       cudaStreamWaitEvent(ss->s[1], ss->fork, 0) != cudaSuccess) {
     set_error("loss_path_step: fork failed: %s", cudaGetErrorString(cudaGetLastError()));
     return (int)cudaErrorUnknown;
@@ -165,4 +168,14 @@ extern "C" int b200ssl_loss_path_step(const b200ssl_step_desc* d, b200ssl_stream
     cudaStreamWaitEvent(main, ss->join[i], 0);
   }
   return rc;
+}
+
+extern "C" int b200ssl_loss_path_fork(b200ssl_stream_t stream) {
+  using namespace b200ssl;
+  SideStreams* ss = side_streams();
+  if (!ss || cudaEventRecord(ss->fork, (cudaStream_t)stream) != cudaSuccess) {
+    set_error("loss_path_fork: %s", cudaGetErrorString(cudaGetLastError()));
+    return (int)cudaErrorUnknown;
+  }
+  return 0;
 }

@@ -123,32 +123,15 @@ class LossPathStep:
                 self._desc, self._desc_key, self._n_seg = d, dkey, n_seg
             d, n_seg = self._desc, self._n_seg
             C.memset(C.byref(d, _lib.StepDesc.noise.offset), 0, C.sizeof(d) - _lib.StepDesc.noise.offset)  # pointers
-            d.serial = 1 if self.serial else 0
+            d.flags = _lib.STEP_SERIAL if self.serial else 0
             d.K = d.image_channels = d.cm_has_ignore = d.cm_label_dtype = 0
             d.cm_ignore_index = 0
             sc = self._get_scratch(scores, d.lovasz, n_seg)
             ns = max(n_seg, 1)
             out = {}
-            # ---- mask + mix (skipped when no images are given)
-            if image_a is not None:
-                require_cuda(image_a, "image_a", torch.float32)
-                p, sigmas = cowmix.draw_mask_parameters(n, self.mask_proportion_range, self.sigma_range)
-                size, taps_dev = cowmix.upload_mask_parameters(p, sigmas, dev)
-                noise = torch.normal(mean=0, std=1, size=(n, 1, h, w), dtype=torch.float32, device=dev)
-                image_a, image_b = image_a.contiguous(), image_b.contiguous()
-                mask = torch.empty_like(noise)
-                mixed_images = torch.empty_like(image_a)
-                d.K, d.image_channels = size, image_a.shape[1]
-                d.noise, d.taps, d.thr_factor = noise.data_ptr(), taps_dev.data_ptr(), taps_dev.data_ptr() + 4 * n * size
-                d.image_a, d.image_b = image_a.data_ptr(), image_b.data_ptr()
-                d.mask, d.mixed_images = mask.data_ptr(), mixed_images.data_ptr()
-                out["mask"], out["mixed_images"] = mask, mixed_images
-                if teacher_a is not None:
-                    teacher_a, teacher_b = teacher_a.contiguous(), teacher_b.contiguous()
-                    mixed_teacher = torch.empty_like(teacher_a)
-                    d.teacher_a, d.teacher_b, d.mixed_teacher = teacher_a.data_ptr(), teacher_b.data_ptr(), mixed_teacher.data_ptr()
-                    out["mixed_teacher"] = mixed_teacher
-                d.ws_cowmix, d.ws_cowmix_bytes = sc["ws_c"].data_ptr(), sc["ws_c"].numel()
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            # Everything the Lovasz / matrix / EMA chains touch is allocated and initialised FIRST, so
+            # that the fork point can be recorded before the mask parameters and the noise are produced.
             # ---- Lovasz
             small = self._small_init.clone()
             grad = torch.empty_like(scores)
@@ -183,8 +166,33 @@ class LossPathStep:
                     table, entries = self._ema.prepare(ema_params, params)
                 if entries:
                     d.ema_table, d.ema_entries, d.ema_alpha = table, entries, float(self.ema_alpha)
+            # ---- mask + mix (skipped when no images are given)
+            if image_a is not None:
+                require_cuda(image_a, "image_a", torch.float32)
+                image_a, image_b = image_a.contiguous(), image_b.contiguous()
+                mask = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev)
+                mixed_images = torch.empty_like(image_a)
+                if teacher_a is not None:
+                    teacher_a, teacher_b = teacher_a.contiguous(), teacher_b.contiguous()
+                    mixed_teacher = torch.empty_like(teacher_a)
+                    d.teacher_a, d.teacher_b, d.mixed_teacher = teacher_a.data_ptr(), teacher_b.data_ptr(), mixed_teacher.data_ptr()
+                    out["mixed_teacher"] = mixed_teacher
+                if not self.serial:
+                    # fork point: the Lovasz / EMA chains need neither the mask parameters nor the noise
+                    with torch.cuda.device(dev):
+                        check(lib.b200ssl_loss_path_fork(stream), "loss_path_fork")
+                    d.flags |= _lib.STEP_PREFORKED
+                p, sigmas = cowmix.draw_mask_parameters(n, self.mask_proportion_range, self.sigma_range)
+                size, taps_dev = cowmix.upload_mask_parameters(p, sigmas, dev)
+                noise = torch.normal(mean=0, std=1, size=(n, 1, h, w), dtype=torch.float32, device=dev)
+                d.K, d.image_channels = size, image_a.shape[1]
+                d.noise, d.taps, d.thr_factor = noise.data_ptr(), taps_dev.data_ptr(), taps_dev.data_ptr() + 4 * n * size
+                d.image_a, d.image_b = image_a.data_ptr(), image_b.data_ptr()
+                d.mask, d.mixed_images = mask.data_ptr(), mixed_images.data_ptr()
+                out["mask"], out["mixed_images"] = mask, mixed_images
+                d.ws_cowmix, d.ws_cowmix_bytes = sc["ws_c"].data_ptr(), sc["ws_c"].numel()
             with torch.cuda.device(dev):
-                check(lib.b200ssl_loss_path_step(C.byref(d), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                check(lib.b200ssl_loss_path_step(C.byref(d), stream),
                       "loss_path_step")
             out["loss"], out["grad"], out["labels"] = small[0], grad, labels
             return out
