@@ -172,16 +172,24 @@ def run_b200(args, rank, world, local_rank):
     inp = make_inputs(device, rank)
     P = W["n"] * W["h"] * W["w"]
     n_params = sum(p.numel() for p in inp["params"])
+    # Multi-GPU: the batch shards by image, the only exchange is [confusion matrix || loss]
+    # once per step.  It goes over NVLink peer memory (b200ssl_peer_*: posted by the step itself, collected
+    # on the communicator's stream, no NCCL call on the data path); if the box cannot map peer memory
+    # every rank falls back to ONE torch.distributed all-reduce per step (the choice is collective).
+    peer = reducer = None
+    if world > 1:
+        peer = b200ssl.utils.make_peer_all_reduce(W["c"] * W["c"], 1, device)
+        if peer is None:
+            reducer = b200ssl.utils.StepReducer(W["c"], 1, device, backend="dist")
     step = b200ssl.LossPathStep(num_classes=W["c"], mask_proportion_range=W["p_range"],
-                                sigma_range=W["sigma_range"], ema_alpha=W["alpha"], mode="binary")
+                                sigma_range=W["sigma_range"], ema_alpha=W["alpha"], mode="binary", peer=peer)
     step.bind_parameters(inp["params"], inp["ema_params"])     # like constructing an optimizer over the lists
-    reducer = b200ssl.utils.StepReducer(W["c"], 1, device)
     torch.manual_seed(0)            # the reference seeds every rank with 0 (distributed_trainer.py:17)
 
     def one_step():
         out = step(inp["image_a"], inp["image_b"], inp["teacher_a"], inp["teacher_b"], inp["scores"],
                    inp["target"], inp["params"], inp["ema_params"])
-        if world > 1:
+        if reducer is not None:
             reducer.all_reduce(out["cm"], [out["loss"]])
         return out
 
@@ -196,11 +204,24 @@ def run_b200(args, rank, world, local_rank):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    # Every warm-up step of a multi-rank run contains a collective, so all ranks must run the SAME
+    # number of steps: the "long enough" decision is taken in chunks and agreed on by all ranks (a
+    # purely time-based loop per rank desynchronises the collective sequence and hangs the job).
     t_w = time.perf_counter()
     n_w = 0
-    while n_w < max(args.warmup, 3) or (time.perf_counter() - t_w) < 1.2:
-        one_step()          # never synchronised: the caching allocator must reach its run-ahead steady state
-        n_w += 1
+    chunk = max(args.warmup, 3)
+    while True:
+        for _ in range(chunk):
+            one_step()      # never synchronised: the caching allocator must reach its run-ahead steady state
+        n_w += chunk
+        done = (time.perf_counter() - t_w) >= 1.2
+        if world > 1:
+            flag = torch.tensor([1 if done else 0], device=device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            done = bool(int(flag))
+        if done:
+            break
+        chunk = 200
     sync_all()
 
     # ---- timed region: K steps, device-resident inputs ----
@@ -294,7 +315,10 @@ def run_b200(args, rank, world, local_rank):
             o = step(b["image_a"], b["image_b"], b["teacher_a"], b["teacher_b"], b["scores"], b["target"],
                      inp["params"], inp["ema_params"])
             consumed[sl].record(main_stream)
-            if world > 1:
+            if peer is not None:
+                peer.result()                            # main stream waits for this step's collect
+                packed = torch.cat([o["loss_sum"].reshape(1), o["cm_sum"].reshape(-1).to(torch.float64)])
+            elif reducer is not None:
                 cm, scs = reducer.all_reduce(o["cm"], [o["loss"]])
                 packed = torch.cat([scs.reshape(-1)[:1], cm.reshape(-1).to(torch.float64)])
             else:
@@ -314,6 +338,19 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(ms), float(ms_e2e)
+    if peer is not None:
+        # a wait that timed out anywhere invalidates the run on every rank (checked collectively)
+        try:
+            peer.status()
+            bad = 0
+        except Exception as e:   # noqa: BLE001
+            print(f"[rank {rank}] {e}", file=sys.stderr)
+            bad = 1
+        flag = torch.tensor([bad], device=device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        peer.close()
+        if int(flag):
+            raise RuntimeError("the NVLink peer exchange timed out on at least one rank; results are invalid")
     if rank != 0:
         return None
 
@@ -349,13 +386,17 @@ def run_b200(args, rank, world, local_rank):
                         "see roofline.stages and DESIGN.md for its FMA-rate fraction")
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": n_w, "ms_per_step": round(ms / args.steps, 4),
+        "warmup": args.warmup, "warmup_steps_run": n_w, "ms_per_step": round(ms / args.steps, 4),
         "ms_per_step_runs": [round(x / args.steps, 4) for x in region_ms], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": W["name"], "pixels_per_gpu_step": P, "classes": W["c"],
                    "ema_params": n_params, "ema_tensors": len(inp["params"]),
                    "lovasz": "losses.binary_lovasz_loss_with_logits (per image, class 1)",
                    "sigma_range": list(W["sigma_range"]), "parallelism": f"dp{world}",
+                   "collective": ("none (single GPU)" if world == 1 else
+                                  "one-shot exchange of [cm || loss] over NVLink peer memory per step "
+                                  "(b200ssl_peer_*), collected lazily" if peer is not None else
+                                  "one torch.distributed (NCCL) all_reduce of [cm || loss] per step"),
                    "l2": "no flush: the 234 MB of step inputs (+268 MB outputs/workspace) exceed the 126 MB L2"},
         "clocks": clock_info,
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,

@@ -18,7 +18,8 @@
  *     stream (cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream).  The only
  *     resources it creates are two internal non-blocking streams and three events
  *     per device for the fork/join inside b200ssl_loss_path_step, and the CUDA events
- *     of the optional profiler.
+ *     of the optional profiler.  The one exception to "allocates nothing" is the 2 MB peer mailbox
+ *     of b200ssl_peer_create (it has to be exportable through CUDA IPC).
  *   - 16-byte aligned bases take the 128-bit path; other alignments fall back to
  *     scalar accesses inside the same kernel (never an error).
  */
@@ -40,6 +41,7 @@ extern "C" {
 #define B200SSL_EINVAL (-1)    /* bad argument */
 #define B200SSL_EWORKSPACE (-2) /* workspace too small */
 #define B200SSL_EUNSUPPORTED (-3)
+#define B200SSL_ETIMEOUT (-4)    /* a peer exchange gave up waiting (b200ssl_peer_status) */
 
 typedef void* b200ssl_stream_t; /* cudaStream_t */
 
@@ -293,6 +295,55 @@ int b200ssl_consistency_backward(const float* student, const float* teacher, int
                                  float* grad_student, b200ssl_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Per-step all-reduce over NVLink peer memory.  Replaces utils/utils.py:43-54
+ * reduce_tensor, which the reference calls 4-6 times per step on single scalars (train.py:53,58,109,
+ * 113,178,181), by ONE exchange of [n_ints int64 counts || n_floats fp32 scalars]: every rank stores
+ * its words straight into every rank's mailbox (one 8-byte store = 32 payload bits + the step's
+ * sequence number, so data and ready-flag arrive together), and a one-block kernel on each rank adds
+ * the world rows of its own mailbox in rank order (int64 adds / fp64 adds: bit-identical results on all
+ * ranks, counts exact).  No NCCL call is on the data path.
+ *
+ *   b200ssl_peer_create   allocates and zeroes the local mailbox on the current device and returns its
+ *                         CUDA IPC handle (handle_out, B200SSL_PEER_HANDLE_BYTES); synchronises once.
+ *   b200ssl_peer_connect  maps the mailboxes of all ranks from their handles (world x HANDLE_BYTES, in
+ *                         rank order; exchanged by the caller, e.g. torch.distributed.all_gather).
+ *   b200ssl_peer_connect_ptrs  the same for communicators living in ONE process (plain device
+ *                         pointers from b200ssl_peer_mailbox; peer access must already be enabled).
+ *   b200ssl_peer_post     stream-ordered, does not wait for anybody unless it is more than 3 steps
+ *                         ahead of the slowest rank's collect.  floats_host: HOST array of n_floats
+ *                         DEVICE pointers to fp32 scalars.
+ *   b200ssl_peer_collect  sums into ints_out [n_ints] int64 / floats_out [n_floats] fp64.  stream != NULL:
+ *                         runs there.  stream == NULL (lazy): runs on the communicator's own high-priority
+ *                         stream, ordered after `post_stream`; the caller's streams never wait for a
+ *                         slower rank until b200ssl_peer_join(comm, stream) orders `stream` after it.
+ *   b200ssl_peer_allreduce  post + collect on `stream`.
+ *   b200ssl_peer_status   (synchronous) B200SSL_ETIMEOUT if any wait gave up (default 20 s per wait,
+ *                         env B200SSL_PEER_TIMEOUT_MS); results of such a step are undefined.
+ * One exchange in flight per communicator; posts must be issued in the same order on all ranks.
+ * Destroy only after all ranks have finished (barrier first).
+ * --------------------------------------------------------------------------------------------- */
+#define B200SSL_PEER_MAX_RANKS 16
+#define B200SSL_PEER_MAX_WORDS 4096 /* 2*n_ints + n_floats */
+#define B200SSL_PEER_MAX_FLOATS 8
+#define B200SSL_PEER_HANDLE_BYTES 64
+typedef struct b200ssl_peer_comm b200ssl_peer_comm;
+
+int b200ssl_peer_create(int rank, int world, b200ssl_peer_comm** comm_out, unsigned char* handle_out);
+void* b200ssl_peer_mailbox(b200ssl_peer_comm* comm);
+int b200ssl_peer_connect(b200ssl_peer_comm* comm, const unsigned char* handles);
+int b200ssl_peer_connect_ptrs(b200ssl_peer_comm* comm, void* const* mailboxes_host);
+int b200ssl_peer_post(b200ssl_peer_comm* comm, const long long* ints, int n_ints,
+                      const float* const* floats_host, int n_floats, b200ssl_stream_t stream);
+int b200ssl_peer_collect(b200ssl_peer_comm* comm, long long* ints_out, double* floats_out,
+                         b200ssl_stream_t post_stream, b200ssl_stream_t stream);
+int b200ssl_peer_join(b200ssl_peer_comm* comm, b200ssl_stream_t stream);
+int b200ssl_peer_allreduce(b200ssl_peer_comm* comm, const long long* ints, int n_ints,
+                           const float* const* floats_host, int n_floats, long long* ints_out,
+                           double* floats_out, b200ssl_stream_t stream);
+int b200ssl_peer_status(b200ssl_peer_comm* comm);
+int b200ssl_peer_destroy(b200ssl_peer_comm* comm);
+
+/* ---------------------------------------------------------------------------------------------
  * The whole loss path of one semi-supervised step in one call (train.py:65-130 order): mask, fused
  * mix of images + teacher predictions, Lovasz forward/backward (unit upstream gradient), EMA,
  * confusion matrix of (labels, argmax scores).  Chains the entry points above; any stage whose input
@@ -348,6 +399,12 @@ typedef struct b200ssl_step_desc {
   const b200ssl_ema_chunk* ema_table;
   int64_t ema_entries;
   double ema_alpha;
+  /* multi-GPU (optional): when `peer` is set the step ends by posting [cm || loss] to every rank and
+   * queues the collect on the communicator's own stream (lazy: b200ssl_peer_join before reading
+   * peer_cm_out [C*C] int64 / peer_loss_out [1] fp64 = sums over ranks) */
+  struct b200ssl_peer_comm* peer;
+  long long* peer_cm_out;
+  double* peer_loss_out;
 } b200ssl_step_desc;
 
 int b200ssl_loss_path_step(const b200ssl_step_desc* d, b200ssl_stream_t stream);

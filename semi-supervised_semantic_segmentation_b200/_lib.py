@@ -53,7 +53,8 @@ class StepDesc(C.Structure):
                                    "nonzero", "labels_u8")] +
         [("ws_cowmix", C.c_void_p), ("ws_cowmix_bytes", C.c_size_t), ("ws_lovasz", C.c_void_p),
          ("ws_lovasz_bytes", C.c_size_t), ("ema_table", C.c_void_p), ("ema_entries", C.c_int64),
-         ("ema_alpha", C.c_double)])
+         ("ema_alpha", C.c_double), ("peer", C.c_void_p), ("peer_cm_out", C.c_void_p),
+         ("peer_loss_out", C.c_void_p)])
 
 
 # name -> (restype, argtypes); mirrors include/b200ssl.h one to one
@@ -92,7 +93,18 @@ SIGNATURES = {
     "b200ssl_loss_path_step": (_i, [C.POINTER(StepDesc), _vp]),
     "b200ssl_loss_path_fork": (_i, [_vp]),
     "b200ssl_sizeof": (_sz, [_i]),
+    "b200ssl_peer_create": (_i, [_i, _i, C.POINTER(C.c_void_p), _vp]),
+    "b200ssl_peer_mailbox": (_vp, [_vp]),
+    "b200ssl_peer_connect": (_i, [_vp, _vp]),
+    "b200ssl_peer_connect_ptrs": (_i, [_vp, _vp]),
+    "b200ssl_peer_post": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
+    "b200ssl_peer_collect": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "b200ssl_peer_join": (_i, [_vp, _vp]),
+    "b200ssl_peer_allreduce": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "b200ssl_peer_status": (_i, [_vp]),
+    "b200ssl_peer_destroy": (_i, [_vp]),
 }
+PEER_HANDLE_BYTES, PEER_MAX_RANKS, PEER_MAX_WORDS, PEER_MAX_FLOATS, PEER_DEPTH = 64, 16, 4096, 8, 4
 
 
 class B200SSLError(RuntimeError):

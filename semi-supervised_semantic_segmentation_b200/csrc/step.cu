@@ -45,6 +45,9 @@ static SideStreams* side_streams() {
   return &ss;
 }
 
+int peer_post_impl(b200ssl_peer_comm* c, const long long* ints, int n_ints, const float* const* floats_host,
+                   int n_floats, cudaStream_t s);  // peer.cu
+
 }  // namespace b200ssl
 
 static int loss_path_step_on(const b200ssl_step_desc* d, b200ssl_stream_t s_mix, b200ssl_stream_t s_lovasz,
@@ -131,6 +134,16 @@ static int loss_path_step_on(const b200ssl_step_desc* d, b200ssl_stream_t s_mix,
         if (rc) return rc;
       }
     }
+  }
+  // 6. multi-GPU: post [cm || loss] into every rank's mailbox; the collect runs on the communicator's
+  // own stream, so this rank's streams never wait for a slower rank
+  if (d->peer) {
+    B200SSL_REQUIRE(d->scores && d->small, "loss_path_step: the peer exchange needs the Lovasz stage");
+    const float* scalars[1] = {d->small};
+    rc = peer_post_impl(d->peer, d->cm, d->cm ? d->classes * d->classes : 0, scalars, 1, (cudaStream_t)s_lovasz);
+    if (rc) return rc;
+    rc = b200ssl_peer_collect(d->peer, d->peer_cm_out, d->peer_loss_out, s_lovasz, nullptr);
+    if (rc) return rc;
   }
   // 4. EMA over all parameters
   stream = s_ema;

@@ -23,7 +23,8 @@ from . import cowmix, lovasz, mean_teacher
 
 class LossPathStep:
     def __init__(self, num_classes, mask_proportion_range=(0.45, 0.55), sigma_range=(8, 32),
-                 ema_alpha=0.99, mode="binary", classes="present", per_image=False, ignore=255, serial=False):
+                 ema_alpha=0.99, mode="binary", classes="present", per_image=False, ignore=255, serial=False,
+                 peer=None):
         if mode not in ("binary", "softmax"):
             raise ValueError("mode must be 'binary' (losses.binary_lovasz_loss_with_logits) or 'softmax'")
         self.num_classes = num_classes
@@ -35,6 +36,10 @@ class LossPathStep:
         self.per_image = per_image
         self.ignore = ignore
         self.serial = serial      # True: keep every kernel on the current stream (no internal fork/join)
+        # utils.PeerAllReduce(num_classes**2, 1, device): every step then ends with the exchange of
+        # [confusion matrix || loss] over NVLink peer memory; out["cm_sum"] / out["loss_sum"] are valid
+        # after peer.result()
+        self.peer = peer
         self._ema = mean_teacher.EmaUpdater()
         self._scratch_key = None
         self._scratch = None
@@ -191,6 +196,12 @@ class LossPathStep:
                 d.mask, d.mixed_images = mask.data_ptr(), mixed_images.data_ptr()
                 out["mask"], out["mixed_images"] = mask, mixed_images
                 d.ws_cowmix, d.ws_cowmix_bytes = sc["ws_c"].data_ptr(), sc["ws_c"].numel()
+            if self.peer is not None and want_cm:
+                if self.peer.n_ints != c * c or self.peer.n_floats != 1:
+                    raise ValueError("LossPathStep: peer must be PeerAllReduce(num_classes**2, 1, device)")
+                cm_sum, loss_sum = self.peer.next_outputs()
+                d.peer, d.peer_cm_out, d.peer_loss_out = self.peer.handle, cm_sum.data_ptr(), loss_sum.data_ptr()
+                out["cm_sum"], out["loss_sum"] = cm_sum.view(c, c), loss_sum[0]
             with torch.cuda.device(dev):
                 check(lib.b200ssl_loss_path_step(C.byref(d), stream),
                       "loss_path_step")

@@ -1,0 +1,72 @@
+"""Launched by tests/test_gpu_peer.py under torchrun (2 ranks, one GPU each): the CUDA-IPC wiring of
+the peer all-reduce, StepReducer's collective backend choice, and LossPathStep(peer=...) against the
+NCCL sums of the same values."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    import b200ssl
+    c = 3
+    red = b200ssl.utils.StepReducer(c, 2, dev, backend="peer")
+    assert red.peer is not None
+    gen = torch.Generator().manual_seed(77 + rank)
+    for step in range(25):
+        cm = torch.randint(0, 2**35, (c, c), generator=gen, dtype=torch.int64).to(dev)
+        sc = [torch.randn((), generator=gen).to(dev) for _ in range(2)]
+        want_cm = cm.clone()
+        want_sc = torch.stack(sc).double()
+        dist.all_reduce(want_cm)
+        dist.all_reduce(want_sc)
+        if step % 2:
+            got_cm, got_sc = red.all_reduce(cm, sc)
+        else:
+            _, h = red.all_reduce(cm, sc, async_op=True)
+            h.wait()
+            got_cm, got_sc = red.result()
+        torch.cuda.synchronize(dev)
+        assert torch.equal(got_cm, want_cm), (rank, step)
+        assert torch.allclose(got_sc, want_sc, rtol=1e-15, atol=0), (rank, step, got_sc, want_sc)
+    red.peer.status()
+
+    # the step entry with the exchange attached
+    g = torch.Generator().manual_seed(5 + rank)
+    n, cc, h, w = 2, 2, 64, 64
+    peer = b200ssl.utils.PeerAllReduce(cc * cc, 1, dev)
+    step = b200ssl.LossPathStep(num_classes=cc, sigma_range=(2, 4), peer=peer)
+    img = [torch.rand(n, 3, h, w, generator=g).to(dev) for _ in range(2)]
+    tea = [torch.randn(n, cc, h, w, generator=g).to(dev) for _ in range(2)]
+    scores = (torch.randn(n, cc, h, w, generator=g) * 3).to(dev)
+    blob = torch.nn.functional.avg_pool2d(torch.randn(n, cc, h, w, generator=g), 9, 1, 4)
+    target = torch.nn.functional.one_hot(blob.argmax(1), cc).permute(0, 3, 1, 2).float().contiguous().to(dev)
+    params, ema = [torch.randn(100, generator=g).to(dev)], [torch.randn(100, generator=g).to(dev)]
+    for _ in range(9):
+        out = step(img[0], img[1], tea[0], tea[1], scores, target, params, ema)
+        peer.result()
+        want_cm = out["cm"].clone()
+        want_loss = out["loss"].double().reshape(1).clone()
+        dist.all_reduce(want_cm)
+        dist.all_reduce(want_loss)
+        torch.cuda.synchronize(dev)
+        assert torch.equal(out["cm_sum"], want_cm), rank
+        assert torch.allclose(out["loss_sum"].reshape(1), want_loss, rtol=1e-15, atol=0), rank
+    peer.status()
+    peer.close()
+    red.peer.close()
+    dist.barrier()
+    if rank == 0:
+        print("peer_worker ok", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
