@@ -295,6 +295,50 @@ int b200ssl_consistency_backward(const float* student, const float* teacher, int
                                  float* grad_student, b200ssl_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Row N4: multi-tensor gradient clip + SGD step + EMA epilogue.
+ *   train.py:122 clip_grad_norm_(params, gradient_clip_value) -> b200ssl_grad_norm_multi (+ _grad_scale_multi
+ *                when the scaled gradients themselves are wanted)
+ *   train.py:123-124 optimizer.step(); optimizer.zero_grad()  (torch.optim.SGD, configs/default_config.py:151)
+ *   train.py:130 / mean_teacher.py:10-11 EMA of the UPDATED parameters
+ *                -> b200ssl_sgd_ema_multi: one launch, p/g/momentum/teacher read once.
+ * The chunk table is built like the EMA table (chunks of B200SSL_EMA_CHUNK elements); momentum / ema
+ * pointer arrays may be NULL (no momentum buffer / no teacher).  norm_and_coef_out: fp32[2] =
+ * {total L2 norm of all gradients, min(max_norm / (norm + 1e-6), 1)} -- torch's clip coefficient, which
+ * b200ssl_sgd_ema_multi applies to every gradient when coef_dev points at norm_and_coef_out + 1
+ * (coef_dev NULL: no clipping).  Arithmetic is torch's, op for op (see csrc/optim.cu).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct b200ssl_sgd_chunk {
+  float* param;
+  float* grad;
+  float* momentum; /* may be NULL */
+  float* ema;      /* may be NULL */
+  int32_t count;
+  int32_t tensor;
+} b200ssl_sgd_chunk;
+
+typedef struct b200ssl_sgd_hyper {
+  double lr, momentum, dampening, weight_decay;
+  double ema_alpha;   /* < 0: no EMA */
+  int32_t nesterov;
+  int32_t first_step; /* momentum buffers are uninitialised: buf = grad (torch clones the gradient) */
+  int32_t zero_grad;  /* also write zeros to the gradients (optimizer.zero_grad(set_to_none=False)) */
+  int32_t reserved_;
+} b200ssl_sgd_hyper;
+
+int64_t b200ssl_sgd_build_table_host(void* const* param_ptrs_host, void* const* grad_ptrs_host,
+                                     void* const* momentum_ptrs_host, void* const* ema_ptrs_host,
+                                     const int64_t* numels_host, int n_tensors,
+                                     b200ssl_sgd_chunk* table_host, int64_t table_capacity);
+size_t b200ssl_grad_norm_workspace_bytes(int64_t n_entries);
+int b200ssl_grad_norm_multi(const b200ssl_sgd_chunk* table_dev, int64_t n_entries, double max_norm,
+                            float* norm_and_coef_out, void* workspace, size_t workspace_bytes,
+                            b200ssl_stream_t stream);
+int b200ssl_grad_scale_multi(const b200ssl_sgd_chunk* table_dev, int64_t n_entries, const float* coef_dev,
+                             b200ssl_stream_t stream);
+int b200ssl_sgd_ema_multi(const b200ssl_sgd_chunk* table_dev, int64_t n_entries, const float* coef_dev,
+                          const b200ssl_sgd_hyper* hyper, b200ssl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Per-step all-reduce over NVLink peer memory.  Replaces utils/utils.py:43-54
  * reduce_tensor, which the reference calls 4-6 times per step on single scalars (train.py:53,58,109,
  * 113,178,181), by ONE exchange of [n_ints int64 counts || n_floats fp32 scalars]: every rank stores

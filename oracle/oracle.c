@@ -207,6 +207,52 @@ ORC_API void orc_ema(float* ema, const float* param, long long n, double alpha) 
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Row N4: train.py:122-124,130 -- clip_grad_norm_ -> torch.optim.SGD.step -> EMA, per element:
+ *   g = RN(g*coef) (only when clipping); g = fmaf(p, wd, g) (wd != 0);
+ *   b = first ? g : fmaf(g, 1-damp, RN(b*mu)); d = nesterov ? fmaf(b, mu, g) : b  (mu != 0);
+ *   p = fmaf(d, -lr, p);  e = fmaf(p, 1-alpha, RN(e*alpha)) (alpha >= 0).
+ * torch/optim/sgd.py _single_tensor_sgd / _multi_tensor_sgd; every add(alpha=) is one fma [probed
+ * bit for bit against torch.optim.SGD, foreach on and off, tests/golden/sgd.npz].
+ * ------------------------------------------------------------------------------------------ */
+ORC_API void orc_sgd_ema(float* p, const float* g, float* buf, float* ema, long long n, int use_coef,
+                         float coef, double lr, double mu, double damp, double wd, double alpha,
+                         int nesterov, int first) {
+  const float neg_lr = (float)(-lr), muf = (float)mu, omd = (float)(1.0 - damp), wdf = (float)wd;
+  const float a = (float)alpha, b1 = (float)(1.0 - alpha);
+  for (long long i = 0; i < n; ++i) {
+    float gi = use_coef ? g[i] * coef : g[i];
+    if (wd != 0.0) gi = fmaf(p[i], wdf, gi);
+    float d = gi;
+    if (mu != 0.0) {
+      float b = first ? gi : fmaf(gi, omd, buf[i] * muf);
+      buf[i] = b;
+      d = nesterov ? fmaf(b, muf, gi) : b;
+    }
+    p[i] = fmaf(d, neg_lr, p[i]);
+    if (alpha >= 0.0 && ema) {
+      const float t = ema[i] * a;
+      ema[i] = fmaf(p[i], b1, t);
+    }
+  }
+}
+
+/* sum of squares in double, sequential (the "exact" value the norm kernels are compared with) */
+ORC_API double orc_sqnorm(const float* g, long long n) {
+  double acc = 0.0;
+  for (long long i = 0; i < n; ++i) acc += (double)g[i] * (double)g[i];
+  return acc;
+}
+
+/* torch.nn.utils.clip_grad_norm_: clip_coef = max_norm / (total_norm + 1e-6) with a tensor total_norm,
+ * i.e. reciprocal(total_norm + 1e-6) * max_norm in fp32, clamped to <= 1 [probed]. */
+ORC_API float orc_clip_coef(float total_norm, double max_norm) {
+  const float t = total_norm + 1e-6f;
+  const float r = 1.0f / t;
+  const float c = r * (float)max_norm;
+  return c < 1.0f ? c : (c != c ? c : 1.0f);
+}
+
+/* ------------------------------------------------------------------------------------------
  * Confusion matrix (restated oracle): bincount(label*D + pred) over pixels whose
  * label != ignore.  other_bucket: D = C+1 and out-of-range values go to row/column C; otherwise
  * D = C and pixels with an out-of-range label or prediction are dropped (and counted).

@@ -11,7 +11,7 @@ hyphen.  Modules mirror the reference's namespaces so that
 is the whole patch to train.py / losses.py.
 """
 from . import _lib            # raises ImportError if the CUDA library has not been built
-from . import cowmix, lovasz, mean_teacher, metrics, losses, utils, consistency  # noqa: F401
+from . import cowmix, lovasz, mean_teacher, metrics, losses, utils, consistency, optim  # noqa: F401
 from .step import LossPathStep  # noqa: F401
 
 __version__ = "0.1.0"

@@ -35,6 +35,17 @@ class EmaChunk(C.Structure):
     _fields_ = [("ema", C.c_void_p), ("param", C.c_void_p), ("count", C.c_int32), ("pad_", C.c_int32)]
 
 
+class SgdChunk(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("momentum", C.c_void_p), ("ema", C.c_void_p),
+                ("count", C.c_int32), ("tensor", C.c_int32)]
+
+
+class SgdHyper(C.Structure):
+    _fields_ = [("lr", C.c_double), ("momentum", C.c_double), ("dampening", C.c_double), ("weight_decay", C.c_double),
+                ("ema_alpha", C.c_double), ("nesterov", C.c_int32), ("first_step", C.c_int32), ("zero_grad", C.c_int32),
+                ("reserved_", C.c_int32)]
+
+
 _vp, _i, _i64, _sz, _d = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
 
 STEP_BINARY, STEP_SOFTMAX = 0, 1
@@ -93,6 +104,11 @@ SIGNATURES = {
     "b200ssl_loss_path_step": (_i, [C.POINTER(StepDesc), _vp]),
     "b200ssl_loss_path_fork": (_i, [_vp]),
     "b200ssl_sizeof": (_sz, [_i]),
+    "b200ssl_sgd_build_table_host": (_i64, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i64]),
+    "b200ssl_grad_norm_workspace_bytes": (_sz, [_i64]),
+    "b200ssl_grad_norm_multi": (_i, [_vp, _i64, _d, _vp, _vp, _sz, _vp]),
+    "b200ssl_grad_scale_multi": (_i, [_vp, _i64, _vp, _vp]),
+    "b200ssl_sgd_ema_multi": (_i, [_vp, _i64, _vp, C.POINTER(SgdHyper), _vp]),
     "b200ssl_peer_create": (_i, [_i, _i, C.POINTER(C.c_void_p), _vp]),
     "b200ssl_peer_mailbox": (_vp, [_vp]),
     "b200ssl_peer_connect": (_i, [_vp, _vp]),
@@ -125,7 +141,7 @@ def _load():
 
 
 lib = _load()
-for _which, _struct in enumerate((EmaChunk, LovaszDesc, StepDesc)):
+for _which, _struct in enumerate((EmaChunk, LovaszDesc, StepDesc, SgdChunk, SgdHyper)):
     if lib.b200ssl_sizeof(_which) != C.sizeof(_struct):
         raise ImportError(f"b200ssl: ctypes layout of {_struct.__name__} ({C.sizeof(_struct)} B) does not match "
                           f"libb200ssl.so ({lib.b200ssl_sizeof(_which)} B); rebuild the library")

@@ -72,6 +72,8 @@ size_t b200ssl_sizeof(int which) {
     case 0: return sizeof(b200ssl_ema_chunk);
     case 1: return sizeof(b200ssl_lovasz_desc);
     case 2: return sizeof(b200ssl_step_desc);
+    case 3: return sizeof(b200ssl_sgd_chunk);
+    case 4: return sizeof(b200ssl_sgd_hyper);
     default: return 0;
   }
 }

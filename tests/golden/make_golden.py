@@ -234,7 +234,61 @@ def consistency_case():
     save("consistency", **out)
 
 
+def sgd_case():
+    """Row N4: train.py:121-130 -- clip_grad_norm_ -> SGD.step() -> zero_grad() -> update_ema_variables,
+    executed with torch's own optimizer / clip function and the reference's EMA function."""
+    gen = torch.Generator().manual_seed(77)
+    shapes = [(1,), (3,), (17, 5), (4, 3, 3, 3), (1025,), (4097,)]
+    params0 = [torch.randn(s, generator=gen) for s in shapes]
+    ema0 = [torch.randn(s, generator=gen) for s in shapes]
+    grads = [[torch.randn(s, generator=gen) * (0.02 if step == 1 else 1.5) for s in shapes] for step in range(3)]
+
+    class M(torch.nn.Module):
+        def __init__(self, ts):
+            super().__init__()
+            self.ps = torch.nn.ParameterList([torch.nn.Parameter(t.clone()) for t in ts])
+
+    out = {"n": len(shapes), "steps": 3}
+    for i, (p, e) in enumerate(zip(params0, ema0)):
+        out[f"param0_{i}"], out[f"ema0_{i}"] = p.numpy(), e.numpy()
+    for step in range(3):
+        for i, g in enumerate(grads[step]):
+            out[f"grad{step}_{i}"] = g.numpy()
+    base_lr = 0.0001 * 1 / 4 * 9                               # configs/default_config.py:139
+    variants = {"default": dict(lr=base_lr, momentum=0.9, weight_decay=0.0005, clip=5.0, alpha=0.99),
+                "nesterov": dict(lr=0.05, momentum=0.8, weight_decay=0.0, nesterov=True, clip=None, alpha=0.999),
+                "plain": dict(lr=0.1, momentum=0.0, weight_decay=0.01, clip=0.5, alpha=0.5),
+                "damp": dict(lr=0.01, momentum=0.9, dampening=0.25, weight_decay=0.001, clip=1e9, alpha=0.99)}
+    for name, v in variants.items():
+        v = dict(v)
+        clip, alpha = v.pop("clip"), v.pop("alpha")
+        student, teacher = M(params0), M(ema0)
+        ref_mt.detach_model_parameters(teacher)
+        opt = torch.optim.SGD(student.parameters(), **v)
+        for step in range(3):
+            for p, g in zip(student.parameters(), grads[step]):
+                p.grad = g.clone()
+            if clip is not None:
+                tn = torch.nn.utils.clip_grad_norm_(student.parameters(), clip)    # train.py:122
+                out[f"{name}_norm{step}"] = tn.numpy()
+            opt.step()                                                                # train.py:123
+            opt.zero_grad()                                                           # train.py:124
+            ref_mt.update_ema_variables(student, teacher, alpha)                      # train.py:130
+            if step != 2:
+                continue                                   # only the state after the last step is stored
+            for i, (p, e) in enumerate(zip(student.parameters(), teacher.parameters())):
+                out[f"{name}_s{step}_param{i}"] = p.detach().numpy().copy()
+                out[f"{name}_s{step}_ema{i}"] = e.detach().numpy().copy()
+                if v.get("momentum", 0.0) != 0.0:
+                    out[f"{name}_s{step}_mom{i}"] = opt.state[p]["momentum_buffer"].numpy().copy()
+    save("sgd", **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:                       # regenerate selected files only: make_golden.py sgd_case ...
+        for fn in sys.argv[1:]:
+            globals()[fn]()
+        sys.exit(0)
     cowmix_case("cowmix_small", 3, 40, 56, (0.4, 0.6), (1.0, 3.0), seed=3)
     cowmix_case("cowmix_c1", 2, 256, 256, (0.45, 0.55), (8, 32), seed=0)      # BASELINE configs[0]
     lovasz_cases()

@@ -225,3 +225,40 @@ def test_consistency_oracle_vs_golden():
         ref = g[f"{tag}_grad"]
         assert np.linalg.norm(grad - ref) <= 1e-5 * np.linalg.norm(ref)
         assert np.array_equal(grad == 0, ref == 0)                 # same confident pixels
+
+
+# ------------------------------------------------------------------------------------------------
+# Row N4: clip_grad_norm_ -> SGD.step -> EMA (train.py:122-130), golden = torch.optim.SGD + the
+# reference's update_ema_variables executed in the build container
+# ------------------------------------------------------------------------------------------------
+SGD_VARIANTS = {"default": dict(lr=0.0001 / 4 * 9, momentum=0.9, weight_decay=0.0005, clip=5.0, alpha=0.99),
+                "nesterov": dict(lr=0.05, momentum=0.8, weight_decay=0.0, nesterov=True, clip=None, alpha=0.999),
+                "plain": dict(lr=0.1, momentum=0.0, weight_decay=0.01, clip=0.5, alpha=0.5),
+                "damp": dict(lr=0.01, momentum=0.9, dampening=0.25, weight_decay=0.001, clip=1e9, alpha=0.99)}
+
+
+@pytest.mark.parametrize("name", list(SGD_VARIANTS))
+def test_sgd_ema_oracle_matches_torch_bit_for_bit(name):
+    g = load_golden("sgd")
+    v = dict(SGD_VARIANTS[name])
+    clip, alpha = v.pop("clip"), v.pop("alpha")
+    n = int(g["n"])
+    params = [g[f"param0_{i}"].copy() for i in range(n)]
+    ema = [g[f"ema0_{i}"].copy() for i in range(n)]
+    moms = [np.zeros_like(p) for p in params] if v.get("momentum", 0.0) else None
+    for step in range(3):
+        grads = [g[f"grad{step}_{i}"] for i in range(n)]
+        coef = None
+        if clip is not None:
+            ref_norm = np.float32(g[f"{name}_norm{step}"])
+            ours = oracle.grad_total_norm(grads)
+            assert abs(float(ours) - float(ref_norm)) <= 1e-6 * float(ref_norm)
+            # the coefficient formula is pinned on torch's own norm; the fp64-accumulated norm may differ
+            # from torch's fp32 norm-of-norms in the last bit
+            coef = oracle.clip_coef(ref_norm, clip)
+        oracle.sgd_ema_step(params, grads, moms, ema, first_step=(step == 0), coef=coef, ema_alpha=alpha, **v)
+    for i in range(n):
+        assert np.array_equal(params[i].view(np.uint32), g[f"{name}_s2_param{i}"].view(np.uint32)), (name, i)
+        assert np.array_equal(ema[i].view(np.uint32), g[f"{name}_s2_ema{i}"].view(np.uint32)), (name, i)
+        if moms is not None:
+            assert np.array_equal(moms[i].view(np.uint32), g[f"{name}_s2_mom{i}"].view(np.uint32)), (name, i)
