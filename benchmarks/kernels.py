@@ -51,8 +51,9 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(0)
     out = {"peak_GBps": PEAK}
 
+    only_optim = "--only-optim" in sys.argv
     # ---- configs[4]: 19-class confusion matrix over 1024x2048 masks, chunks of 32 masks (> L2)
-    n, h, w, c = 32, 1024, 2048, 19
+    n, h, w, c = (1, 64, 64, 19) if only_optim else (32, 1024, 2048, 19)
     lab = coherent(n, c, h, w, gen)
     wrong = coherent(n, 5, h, w, gen) == 0                      # ~20 % of the area, in blobs
     prd = torch.where(wrong, coherent(n, c, h, w, gen), lab)    # predictions agree except in blobs
@@ -64,7 +65,7 @@ def main():
         bytes_ = 2 * l.numel() * l.element_size()
         out[f"cm_{name}_19c_32x1024x2048"] = {"ms": round(ms, 4), "Gpix_s": round(l.numel() / ms / 1e6, 2),
                                              "GBps": round(bytes_ / ms / 1e6, 1), "frac": round(bytes_ / ms / 1e6 / PEAK, 3)}
-    logits = torch.randn(8, c, h, w, device=dev, generator=gen)
+    logits = torch.randn(min(8, n), c, h, w, device=dev, generator=gen)
     l8 = lab[:8].to(torch.uint8)
     ms = timeit(lambda: b200ssl.metrics.confusion_matrix_from_logits(logits, l8, ignore_index=255))
     bytes_ = logits.numel() * 4 + l8.numel()
@@ -73,7 +74,7 @@ def main():
     del logits, lab, prd
 
     # ---- EMA parameter sets
-    for key in ["unet_mnv2_c2", "simple_unet_c2", "deeplabv3_r101_c21"]:
+    for key in ([] if only_optim else ["unet_mnv2_c2", "simple_unet_c2", "deeplabv3_r101_c21"]):
         shapes = bench.load_param_shapes(key)
         ps = [torch.randn(s, device=dev, generator=gen) for s in shapes]
         es = [torch.randn(s, device=dev, generator=gen) for s in shapes]
@@ -89,6 +90,39 @@ def main():
         ms_ref = timeit(ref, reps=3, warm=1, inner=2)
         out[f"ema_{key}"]["torch_cuda_ref_ms"] = round(ms_ref, 4)
         del ps, es
+
+    # ---- row N4: clip_grad_norm_ + SGD.step + zero_grad + EMA (train.py:122-130), fused vs torch's own
+    # foreach CUDA path on the same GPU
+    for key in ["unet_mnv2_c2", "deeplabv3_r101_c21"]:
+        shapes = bench.load_param_shapes(key)
+        ps = [torch.nn.Parameter(torch.randn(s, device=dev, generator=gen)) for s in shapes]
+        es = [torch.randn(s, device=dev, generator=gen) for s in shapes]
+        gs = [torch.randn(s, device=dev, generator=gen) for s in shapes]
+        for p, g in zip(ps, gs):
+            p.grad = g
+        opt = b200ssl.optim.FusedSGD(ps, lr=2.25e-4, momentum=0.9, weight_decay=5e-4)
+        ms = timeit(lambda: opt.step(max_grad_norm=5.0, ema_params=es, ema_alpha=0.99, zero_grad=False))
+        npar = sum(p.numel() for p in ps)
+        alg = (4 + 28) * npar                     # norm pass reads g; update reads p,g,b,e and writes p,b,e
+        ref_ps = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+        for p, g in zip(ref_ps, gs):
+            p.grad = g.clone()
+        ref_opt = torch.optim.SGD(ref_ps, lr=2.25e-4, momentum=0.9, weight_decay=5e-4)
+        ref_es = [e.clone() for e in es]
+
+        def ref():
+            torch.nn.utils.clip_grad_norm_(ref_ps, 5.0)
+            ref_opt.step()
+            for e, p in zip(ref_es, ref_ps):
+                e.mul_(0.99).add_(p.data, alpha=1 - 0.99)
+        ms_ref = timeit(ref, reps=3, warm=1, inner=2)
+        out[f"sgd_clip_ema_{key}"] = {"params": npar, "tensors": len(ps), "ms": round(ms, 4),
+                                      "GBps": round(alg / ms / 1e6, 1), "frac": round(alg / ms / 1e6 / PEAK, 3),
+                                      "torch_cuda_ref_ms": round(ms_ref, 4), "speedup": round(ms_ref / ms, 1)}
+        del ps, es, gs, ref_ps, ref_es, opt, ref_opt
+    if "--only-optim" in sys.argv:
+        print(json.dumps(out))
+        return
 
     # ---- multi-class Lovasz forward+backward (fused), configs[2]/[3] class counts
     for (n, c, h, w) in ([(4, 21, 512, 512)] if quick else [(4, 21, 512, 512), (1, 19, 1024, 2048)]):

@@ -295,6 +295,22 @@ int b200ssl_consistency_backward(const float* student, const float* teacher, int
                                  float* grad_student, b200ssl_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Row N2: bilinear up-sampling (F.interpolate(..., mode='bilinear', align_corners=False), train.py:
+ * 71-75,93-94, losses.py:18-19) fused into the mix.  b200ssl_mix2_upsampled is b200ssl_mix2 /
+ * b200ssl_mix2_field with the SECOND tensor pair given at low resolution [n,c1,h_in,w_in]: the
+ * full-resolution teacher predictions are never materialised.  tau == NULL: `mask` is the {0,1} mask
+ * [n,1,h,w]; tau != NULL: `mask` is the smoothed field and the mask is formed and written to mask_out.
+ * b200ssl_upsample_bilinear is the stand-alone interpolation of `planes` = n*c planes.
+ * Bit-identical to ATen's CPU kernel for out >= in (the only direction the reference uses).
+ * --------------------------------------------------------------------------------------------- */
+int b200ssl_mix2_upsampled(const float* a0, const float* b0, float* out0, int c0, const float* a1_lo,
+                           const float* b1_lo, float* out1, int c1, int h_in, int w_in, const float* mask,
+                           const float* tau, float* mask_out, int64_t n, int h, int w,
+                           b200ssl_stream_t stream);
+int b200ssl_upsample_bilinear(const float* in, int64_t planes, int h_in, int w_in, float* out, int h, int w,
+                              b200ssl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Row N4: multi-tensor gradient clip + SGD step + EMA epilogue.
  *   train.py:122 clip_grad_norm_(params, gradient_clip_value) -> b200ssl_grad_norm_multi (+ _grad_scale_multi
  *                when the scaled gradients themselves are wanted)
@@ -449,6 +465,9 @@ typedef struct b200ssl_step_desc {
   struct b200ssl_peer_comm* peer;
   long long* peer_cm_out;
   double* peer_loss_out;
+  /* row N2: teacher_a / teacher_b are [n,classes,teacher_h,teacher_w] and are bilinearly up-sampled to
+   * h x w inside the mix (0 = they are already h x w) */
+  int32_t teacher_h, teacher_w;
 } b200ssl_step_desc;
 
 int b200ssl_loss_path_step(const b200ssl_step_desc* d, b200ssl_stream_t stream);

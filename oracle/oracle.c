@@ -207,6 +207,45 @@ ORC_API void orc_ema(float* ema, const float* param, long long n, double alpha) 
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Row N2: F.interpolate(x, size, mode='bilinear', align_corners=False) (train.py:72-75,93-94,
+ * losses.py:18-19) = ATen upsample_bilinear2d:
+ *   s = max(fmaf(in/out, dst+0.5, -0.5), 0); i0 = min(floor(s), in-1); l = clamp(s-i0, 0, 1)
+ *   v = fmaf(1-ly, fmaf(1-lx, v00, lx*v01), ly*fmaf(1-lx, v10, lx*v11))
+ * [probed: bit-identical to torch 2.11 CPU for out >= in, tests/golden/upsample.npz; down-sampling
+ * takes another ATen code path and agrees to 1 ulp only].
+ * ------------------------------------------------------------------------------------------ */
+ORC_API void orc_upsample_bilinear(const float* in, long long planes, int h, int w, float* out, int H, int W) {
+  const float ry = (float)h / (float)H, rx = (float)w / (float)W;
+  for (long long p = 0; p < planes; ++p) {
+    const float* src = in + (size_t)p * h * w;
+    float* dst = out + (size_t)p * H * W;
+    for (int y = 0; y < H; ++y) {
+      float s = fmaf(ry, (float)y + 0.5f, -0.5f);
+      if (s < 0.f) s = 0.f;
+      int y0 = (int)floorf(s);
+      if (y0 > h - 1) y0 = h - 1;
+      float ly = s - (float)y0;
+      ly = ly < 0.f ? 0.f : (ly > 1.f ? 1.f : ly);
+      const float hy = 1.0f - ly;
+      const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+      for (int x = 0; x < W; ++x) {
+        float t = fmaf(rx, (float)x + 0.5f, -0.5f);
+        if (t < 0.f) t = 0.f;
+        int x0 = (int)floorf(t);
+        if (x0 > w - 1) x0 = w - 1;
+        float lx = t - (float)x0;
+        lx = lx < 0.f ? 0.f : (lx > 1.f ? 1.f : lx);
+        const float hx = 1.0f - lx;
+        const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+        const float t0 = fmaf(hx, src[(size_t)y0 * w + x0], lx * src[(size_t)y0 * w + x1]);
+        const float t1 = fmaf(hx, src[(size_t)y1 * w + x0], lx * src[(size_t)y1 * w + x1]);
+        dst[(size_t)y * W + x] = fmaf(hy, t0, ly * t1);
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
  * Row N4: train.py:122-124,130 -- clip_grad_norm_ -> torch.optim.SGD.step -> EMA, per element:
  *   g = RN(g*coef) (only when clipping); g = fmaf(p, wd, g) (wd != 0);
  *   b = first ? g : fmaf(g, 1-damp, RN(b*mu)); d = nesterov ? fmaf(b, mu, g) : b  (mu != 0);

@@ -65,7 +65,7 @@ class StepDesc(C.Structure):
         [("ws_cowmix", C.c_void_p), ("ws_cowmix_bytes", C.c_size_t), ("ws_lovasz", C.c_void_p),
          ("ws_lovasz_bytes", C.c_size_t), ("ema_table", C.c_void_p), ("ema_entries", C.c_int64),
          ("ema_alpha", C.c_double), ("peer", C.c_void_p), ("peer_cm_out", C.c_void_p),
-         ("peer_loss_out", C.c_void_p)])
+         ("peer_loss_out", C.c_void_p), ("teacher_h", C.c_int32), ("teacher_w", C.c_int32)])
 
 
 # name -> (restype, argtypes); mirrors include/b200ssl.h one to one
@@ -104,6 +104,8 @@ SIGNATURES = {
     "b200ssl_loss_path_step": (_i, [C.POINTER(StepDesc), _vp]),
     "b200ssl_loss_path_fork": (_i, [_vp]),
     "b200ssl_sizeof": (_sz, [_i]),
+    "b200ssl_mix2_upsampled": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i64, _i, _i, _vp]),
+    "b200ssl_upsample_bilinear": (_i, [_vp, _i64, _i, _i, _vp, _i, _i, _vp]),
     "b200ssl_sgd_build_table_host": (_i64, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i64]),
     "b200ssl_grad_norm_workspace_bytes": (_sz, [_i64]),
     "b200ssl_grad_norm_multi": (_i, [_vp, _i64, _d, _vp, _vp, _sz, _vp]),

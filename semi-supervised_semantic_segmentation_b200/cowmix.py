@@ -195,9 +195,22 @@ def mix2_with_mask(a0, b0, a1, b1, mask):
             raise ValueError("a per-channel mask cannot be shared with a second tensor pair")
         a1 = _as_nchw(require_cuda(a1, "tensor_a1", torch.float32))
         b1 = _as_nchw(require_cuda(b1, "tensor_b1", torch.float32))
-        if a1.shape != b1.shape or a1.shape[0] != n or (a1[0, 0].numel() if a1.numel() else 0) != hw:
-            raise ValueError("second tensor pair must share batch and spatial size with the first")
+        if a1.shape != b1.shape or a1.shape[0] != n:
+            raise ValueError("second tensor pair must share the batch size with the first")
         c1 = a1.shape[1]
+        if a1.dim() == 4 and a0.dim() == 4 and a1.shape[2:] != a0.shape[2:]:
+            # row N2: the second pair is at a lower resolution (teacher logits before train.py:72-75's
+            # F.interpolate): it is up-sampled bilinearly (align_corners=False) inside the mix
+            h, w = a0.shape[2], a0.shape[3]
+            out1 = torch.empty((n, c1, h, w), dtype=torch.float32, device=a0.device)
+            with torch.cuda.device(a0.device):
+                check(lib.b200ssl_mix2_upsampled(
+                    a0.data_ptr(), b0.data_ptr(), out0.data_ptr(), c0, a1.data_ptr(), b1.data_ptr(), out1.data_ptr(),
+                    c1, a1.shape[2], a1.shape[3], mask.data_ptr(), None, None, n, h, w, stream_ptr(a0.device)),
+                    "mix2_upsampled")
+            return out0, out1
+        if (a1[0, 0].numel() if a1.numel() else 0) != hw:
+            raise ValueError("second tensor pair must share batch and spatial size with the first")
         out1 = torch.empty_like(a1)
     with torch.cuda.device(a0.device):
         check(lib.b200ssl_mix2(
@@ -206,6 +219,20 @@ def mix2_with_mask(a0, b0, a1, b1, mask):
             out1.data_ptr() if c1 else None, c1, mask.data_ptr(), c0 if per_channel else 1,
             n, hw, stream_ptr(a0.device)), "mix2")
     return out0, out1
+
+
+def upsample_bilinear(x, size):
+    """F.interpolate(x, size, mode='bilinear', align_corners=False) for no-grad consumers (train.py:72-75:
+    teacher predictions): bit-identical to ATen for out >= in.  x: [N,C,h,w] fp32 CUDA."""
+    x = require_cuda(x, "x", torch.float32).contiguous()
+    if x.dim() != 4:
+        raise ValueError("upsample_bilinear expects [N,C,h,w]")
+    h, w = int(size[0]), int(size[1])
+    out = torch.empty((x.shape[0], x.shape[1], h, w), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.b200ssl_upsample_bilinear(x.data_ptr(), x.shape[0] * x.shape[1], x.shape[2], x.shape[3],
+                                            out.data_ptr(), h, w, stream_ptr(x.device)), "upsample_bilinear")
+    return out
 
 
 class _Mix(torch.autograd.Function):

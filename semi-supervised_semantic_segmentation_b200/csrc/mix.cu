@@ -99,7 +99,145 @@ mix2_kernel(const float* __restrict__ a0, const float* __restrict__ b0, float* _
   }
 }
 
+// ---- row N2: bilinear upsampling of the teacher predictions fused into the mix -----------
+// train.py:71-75 materialises F.interpolate(ema_pred, image size, 'bilinear', align_corners=False) for
+// both teacher predictions (a full-resolution [N,C,H,W] write + read each) before mixing them
+// (train.py:82).  Here the mix reads the LOW-resolution predictions (16x fewer bytes at HRNet's stride 4,
+// L2-resident) and interpolates in registers.  Arithmetic = ATen's upsample_bilinear2d, bit for bit on
+// up-sampling and same-size shapes [probed against the CPU kernel]:
+//   s  = max(fma(in/out, dst + 0.5, -0.5), 0);  i0 = min(floor(s), in-1);  l = clamp(s - i0, 0, 1)
+//   v  = fma(1-ly, fma(1-lx, v00, RN(lx*v01)), RN(ly * fma(1-lx, v10, RN(lx*v11))))
+struct AxisTap {
+  int i0, i1;
+  float w0, w1;
+};
+__device__ __forceinline__ AxisTap axis_tap(int dst, int in, float scale) {
+  float s = __fmaf_rn(scale, (float)dst + 0.5f, -0.5f);
+  s = s < 0.f ? 0.f : s;
+  int i0 = (int)floorf(s);
+  i0 = i0 > in - 1 ? in - 1 : i0;
+  float l = __fsub_rn(s, (float)i0);
+  l = l < 0.f ? 0.f : (l > 1.f ? 1.f : l);
+  AxisTap t;
+  t.i0 = i0;
+  t.i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  t.w0 = __fsub_rn(1.0f, l);
+  t.w1 = l;
+  return t;
+}
+__device__ __forceinline__ float bilerp(const float* __restrict__ row0, const float* __restrict__ row1,
+                                        const AxisTap& tx, float wy0, float wy1) {
+  const float t0 = __fmaf_rn(tx.w0, __ldg(row0 + tx.i0), __fmul_rn(tx.w1, __ldg(row0 + tx.i1)));
+  const float t1 = __fmaf_rn(tx.w0, __ldg(row1 + tx.i0), __fmul_rn(tx.w1, __ldg(row1 + tx.i1)));
+  return __fmaf_rn(wy0, t0, __fmul_rn(wy1, t1));
+}
+
+// One thread: VEC consecutive pixels of one output row.  a0/b0 (images) are full resolution; a1/b1 are
+// [n, c1, h_in, w_in].  a1 only (b1 == nullptr, out0 unused): plain up-sampling into out1.
+template <int VEC, bool FIELD>
+__global__ void __launch_bounds__(kMixThreads, 2)
+mix2_upsampled_kernel(const float* __restrict__ a0, const float* __restrict__ b0, float* __restrict__ out0, int c0,
+                      const float* __restrict__ a1, const float* __restrict__ b1, float* __restrict__ out1, int c1,
+                      int h_in, int w_in, const float* __restrict__ mask, long long n, int h, int w,
+                      const float* __restrict__ tau, float* __restrict__ mask_out) {
+  const long long hw = (long long)h * w, hw_in = (long long)h_in * w_in;
+  const int per_row = w / VEC;
+  const long long total = n * h * per_row;
+  const float sy = (float)h_in / (float)h, sx = (float)w_in / (float)w;
+  for (long long q = (long long)blockIdx.x * kMixThreads + threadIdx.x; q < total;
+       q += (long long)gridDim.x * kMixThreads) {
+    const long long row = q / per_row;
+    const int x = (int)(q - row * per_row) * VEC;
+    const long long n_idx = row / h;
+    const int y = (int)(row - n_idx * h);
+    const long long off = (long long)y * w + x;
+    Pack<VEC> m, om;
+    if (mask) {
+      m.load(mask + n_idx * hw + off);
+      if (FIELD) {
+        const float t = __ldg(tau + n_idx);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) m.at(e) = m.at(e) > t ? 1.0f : 0.0f;
+        m.store(mask_out + n_idx * hw + off);
+      }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) om.at(e) = __fsub_rn(1.0f, m.at(e));
+    }
+    if (c0 > 0) mix_tensor<VEC, false>(a0, b0, out0, c0, n_idx, off, hw, m, om, mask);
+    const AxisTap ty = axis_tap(y, h_in, sy);
+    AxisTap tx[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) tx[e] = axis_tap(x + e, w_in, sx);
+    for (int j = 0; j < c1; ++j) {
+      const long long plane = (n_idx * c1 + j) * hw_in;
+      const float* a_r0 = a1 + plane + (long long)ty.i0 * w_in;
+      const float* a_r1 = a1 + plane + (long long)ty.i1 * w_in;
+      Pack<VEC> o;
+      if (b1) {
+        const float* b_r0 = b1 + plane + (long long)ty.i0 * w_in;
+        const float* b_r1 = b1 + plane + (long long)ty.i1 * w_in;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+          o.at(e) = mix_one(bilerp(a_r0, a_r1, tx[e], ty.w0, ty.w1), bilerp(b_r0, b_r1, tx[e], ty.w0, ty.w1),
+                            m.at(e), om.at(e));
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) o.at(e) = bilerp(a_r0, a_r1, tx[e], ty.w0, ty.w1);
+      }
+      o.store(out1 + (n_idx * c1 + j) * hw + off);
+    }
+  }
+}
+
 }  // namespace b200ssl
+
+static int mix2_upsampled_launch(const float* a0, const float* b0, float* out0, int c0, const float* a1,
+                                 const float* b1, float* out1, int c1, int h_in, int w_in, const float* mask,
+                                 const float* tau, float* mask_out, int64_t n, int h, int w,
+                                 b200ssl_stream_t stream, const char* who) {
+  using namespace b200ssl;
+  B200SSL_REQUIRE(n >= 0 && h >= 0 && w >= 0 && c0 >= 0 && c1 >= 0, "%s: negative extent", who);
+  if (n == 0 || h == 0 || w == 0) return 0;
+  B200SSL_REQUIRE(c1 == 0 || (a1 && out1 && h_in >= 1 && w_in >= 1), "%s: null or empty low-resolution tensor", who);
+  B200SSL_REQUIRE(c0 == 0 || (a0 && b0 && out0), "%s: null tensor 0", who);
+  B200SSL_REQUIRE(mask || (!b1 && c0 == 0), "%s: null mask", who);
+  B200SSL_REQUIRE(!tau || mask_out, "%s: null mask_out", who);
+  bool vec = (w % 4 == 0) && aligned16(out1) && (!mask || aligned16(mask));
+  if (c0) vec = vec && aligned16(a0) && aligned16(b0) && aligned16(out0);
+  if (tau) vec = vec && aligned16(mask_out);
+  const long long work = (long long)n * h * (vec ? w / 4 : w);
+  long long blocks = (work + kMixThreads - 1) / kMixThreads;
+  const long long cap = (long long)kNumSMs * 8 * 16;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t s = (cudaStream_t)stream;
+#define LAUNCH(V, F) \
+  mix2_upsampled_kernel<V, F><<<(int)blocks, kMixThreads, 0, s>>>(a0, b0, out0, c0, a1, b1, out1, c1, h_in, w_in, mask, n, \
+                                                                  h, w, tau, mask_out)
+  prof_begin(b1 ? (tau ? "mix2_upsampled_threshold" : "mix2_upsampled") : "upsample_bilinear", s);
+  if (tau) {
+    if (vec) LAUNCH(4, true); else LAUNCH(1, true);
+  } else {
+    if (vec) LAUNCH(4, false); else LAUNCH(1, false);
+  }
+#undef LAUNCH
+  return check_launch(who);
+}
+
+extern "C" int b200ssl_mix2_upsampled(const float* a0, const float* b0, float* out0, int c0, const float* a1_lo,
+                                      const float* b1_lo, float* out1, int c1, int h_in, int w_in,
+                                      const float* mask, const float* tau, float* mask_out, int64_t n, int h, int w,
+                                      b200ssl_stream_t stream) {
+  using namespace b200ssl;
+  B200SSL_REQUIRE(c1 == 0 || b1_lo, "mix2_upsampled: null second low-resolution tensor");
+  return mix2_upsampled_launch(a0, b0, out0, c0, a1_lo, b1_lo, out1, c1, h_in, w_in, mask, tau, mask_out, n, h, w, stream,
+                               "mix2_upsampled");
+}
+
+extern "C" int b200ssl_upsample_bilinear(const float* in, int64_t planes, int h_in, int w_in, float* out, int h, int w,
+                                         b200ssl_stream_t stream) {
+  return mix2_upsampled_launch(nullptr, nullptr, nullptr, 0, in, nullptr, out, 1, h_in, w_in, nullptr, nullptr, nullptr,
+                               planes, h, w, stream, "upsample_bilinear");
+}
 
 static int mix2_launch(const float* a0, const float* b0, float* out0, int c0, const float* a1, const float* b1,
                        float* out1, int c1, const float* mask, int mask_channels, int64_t n, int64_t hw,

@@ -68,8 +68,14 @@ static int loss_path_step_on(const b200ssl_step_desc* d, b200ssl_stream_t s_mix,
     rc = b200ssl_cowmix_field(d->noise, d->taps, d->K, d->thr_factor, d->n, d->h, d->w, field, tau, d->ws_cowmix,
                               d->ws_cowmix_bytes, stream);
     if (rc) return rc;
-    rc = b200ssl_mix2_field(d->image_a, d->image_b, d->mixed_images, d->image_channels, d->teacher_a, d->teacher_b,
-                            d->mixed_teacher, d->teacher_a ? d->classes : 0, field, tau, d->mask, d->n, hw, stream);
+    const bool lowres = d->teacher_a && d->teacher_h > 0 && d->teacher_w > 0 && (d->teacher_h != d->h || d->teacher_w != d->w);
+    if (lowres)
+      rc = b200ssl_mix2_upsampled(d->image_a, d->image_b, d->mixed_images, d->image_channels, d->teacher_a, d->teacher_b,
+                                  d->mixed_teacher, d->classes, d->teacher_h, d->teacher_w, field, tau, d->mask, d->n,
+                                  d->h, d->w, stream);
+    else
+      rc = b200ssl_mix2_field(d->image_a, d->image_b, d->mixed_images, d->image_channels, d->teacher_a, d->teacher_b,
+                              d->mixed_teacher, d->teacher_a ? d->classes : 0, field, tau, d->mask, d->n, hw, stream);
     if (rc) return rc;
   } else {
     if (d->noise) {
@@ -78,8 +84,13 @@ static int loss_path_step_on(const b200ssl_step_desc* d, b200ssl_stream_t s_mix,
       if (rc) return rc;
     }
     if (d->image_a) {
-      rc = b200ssl_mix2(d->image_a, d->image_b, d->mixed_images, d->image_channels, d->teacher_a, d->teacher_b,
-                        d->mixed_teacher, d->teacher_a ? d->classes : 0, d->mask, 1, d->n, hw, stream);
+      if (d->teacher_a && d->teacher_h > 0 && d->teacher_w > 0 && (d->teacher_h != d->h || d->teacher_w != d->w))
+        rc = b200ssl_mix2_upsampled(d->image_a, d->image_b, d->mixed_images, d->image_channels, d->teacher_a,
+                                    d->teacher_b, d->mixed_teacher, d->classes, d->teacher_h, d->teacher_w, d->mask,
+                                    nullptr, nullptr, d->n, d->h, d->w, stream);
+      else
+        rc = b200ssl_mix2(d->image_a, d->image_b, d->mixed_images, d->image_channels, d->teacher_a, d->teacher_b,
+                          d->mixed_teacher, d->teacher_a ? d->classes : 0, d->mask, 1, d->n, hw, stream);
       if (rc) return rc;
     }
   }

@@ -137,56 +137,82 @@ class FusedSGD(torch.optim.Optimizer):
                                       nesterov=nesterov))
         self._tables = [_SgdTable() for _ in self.param_groups]
         self._norm_table = _SgdTable()
+        self._cache = {}
 
     @torch.no_grad()
     def step(self, closure=None, max_grad_norm=None, ema_params=None, ema_alpha=None, zero_grad=False):
         """max_grad_norm: clip_grad_norm_ over ALL parameters of the optimiser first (train.py:122) and
         return the total norm; ema_params (+ ema_alpha): teacher parameters, in the order of the
-        optimiser's parameters, updated from the NEW student values (train.py:130); zero_grad: write
+        optimiser's parameters (pass the same list object every step), updated from the NEW student
+        values (train.py:130); zero_grad: write
         zeros into the gradients (optimizer.zero_grad(set_to_none=False))."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        all_params = [p for g in self.param_groups for p in g["params"]]
-        if ema_params is not None:
-            ema_params = list(ema_params)
-            if len(ema_params) != len(all_params) or ema_alpha is None:
-                raise ValueError("FusedSGD.step: ema_params must match the optimiser's parameters and needs ema_alpha")
-        ema_of = dict(zip(map(id, all_params), ema_params)) if ema_params is not None else None
+        groups = self.param_groups
+        single = len(groups) == 1
+        if ema_params is not None and ema_alpha is None:
+            raise ValueError("FusedSGD.step: ema_params needs ema_alpha")
+        # per-group tensor lists are cached; only the data pointers are re-read every step
+        plan = []
+        offset = 0
+        for gi, group in enumerate(groups):
+            gparams = group["params"]
+            cache = self._cache.get(gi)
+            with_grad = tuple(p.grad is not None for p in gparams)
+            ema_key = id(ema_params) if ema_params is not None else None
+            if cache is None or cache["with_grad"] != with_grad or cache["ema_key"] != ema_key or \
+                    cache["n"] != len(gparams):
+                params = [p for p in gparams if p.grad is not None]
+                moms, first = None, False
+                if group["momentum"] != 0 and params:
+                    fresh = []
+                    moms = []
+                    for p in params:
+                        st = self.state[p]
+                        if st.get("momentum_buffer") is None:
+                            st["momentum_buffer"] = torch.empty_like(p, memory_format=torch.preserve_format)
+                            fresh.append(True)
+                        else:
+                            fresh.append(False)
+                        moms.append(st["momentum_buffer"])
+                    if any(fresh) and not all(fresh):
+                        raise RuntimeError("FusedSGD: parameters of one group must start receiving gradients together")
+                    first = all(fresh)
+                emas = None
+                if ema_params is not None:
+                    if not isinstance(ema_params, (list, tuple)):
+                        raise TypeError("FusedSGD.step: pass ema_params as a list (it is cached by identity)")
+                    if len(ema_params) != sum(len(g["params"]) for g in groups):
+                        raise ValueError("FusedSGD.step: ema_params must match the optimiser's parameters")
+                    emas = [ema_params[offset + k] for k, p in enumerate(gparams) if p.grad is not None]
+                cache = self._cache[gi] = dict(with_grad=with_grad, ema_key=ema_key, n=len(gparams), params=params,
+                                               moms=moms, emas=emas, first=first)
+            else:
+                cache["first"] = False
+            offset += len(gparams)
+            if cache["params"]:
+                plan.append((group, self._tables[gi], cache))
         coef_ptr, total_norm = None, None
-        if max_grad_norm is not None:
-            with_grad = [p for p in all_params if p.grad is not None]
-            if with_grad:
-                self._norm_table.prepare(with_grad, [p.grad for p in with_grad], None, None)
-                self._norm_table.norm(max_grad_norm)
-                coef_ptr = self._norm_table.small.data_ptr() + 4
-                total_norm = self._norm_table.small[0]
-        for group, tab in zip(self.param_groups, self._tables):
-            params = [p for p in group["params"] if p.grad is not None]
-            if not params:
-                continue
-            mu = group["momentum"]
-            first = False
-            moms = None
-            if mu != 0:
-                moms = []
-                for p in params:
-                    st = self.state[p]
-                    if "momentum_buffer" not in st or st["momentum_buffer"] is None:
-                        st["momentum_buffer"] = torch.empty_like(p, memory_format=torch.preserve_format)
-                        st["_b200ssl_fresh"] = True
-                    moms.append(st["momentum_buffer"])
-                fresh = [self.state[p].pop("_b200ssl_fresh", False) for p in params]
-                if any(fresh) and not all(fresh):
-                    raise RuntimeError("FusedSGD: parameters of one group must start receiving gradients together")
-                first = all(fresh)
-            emas = [ema_of[id(p)] for p in params] if ema_of is not None else None
-            tab.prepare(params, [p.grad for p in params], moms, emas)
-            h = _lib.SgdHyper(lr=float(group["lr"]), momentum=float(mu), dampening=float(group["dampening"]),
-                              weight_decay=float(group["weight_decay"]),
-                              ema_alpha=float(ema_alpha) if emas is not None else -1.0,
-                              nesterov=int(bool(group["nesterov"])), first_step=int(first), zero_grad=int(bool(zero_grad)))
+        for group, tab, cache in plan:
+            tab.prepare(cache["params"], [p.grad for p in cache["params"]], cache["moms"], cache["emas"])
+        if max_grad_norm is not None and plan:
+            if single:
+                norm_tab = plan[0][1]                       # the update table already lists every gradient
+            else:
+                norm_tab = self._norm_table
+                every = [p for _, _, c in plan for p in c["params"]]
+                norm_tab.prepare(every, [p.grad for p in every], None, None)
+            norm_tab.norm(max_grad_norm)
+            coef_ptr = norm_tab.small.data_ptr() + 4
+            total_norm = norm_tab.small[0]
+        for group, tab, cache in plan:
+            h = _lib.SgdHyper(lr=float(group["lr"]), momentum=float(group["momentum"]),
+                              dampening=float(group["dampening"]), weight_decay=float(group["weight_decay"]),
+                              ema_alpha=float(ema_alpha) if cache["emas"] is not None else -1.0,
+                              nesterov=int(bool(group["nesterov"])), first_step=int(cache["first"]),
+                              zero_grad=int(bool(zero_grad)))
             with torch.cuda.device(tab.device):
                 check(lib.b200ssl_sgd_ema_multi(tab.table.data_ptr(), tab.entries, coef_ptr, C.byref(h),
                                                 stream_ptr(tab.device)), "sgd_ema_multi")

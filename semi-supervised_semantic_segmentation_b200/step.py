@@ -179,7 +179,12 @@ class LossPathStep:
                 mixed_images = torch.empty_like(image_a)
                 if teacher_a is not None:
                     teacher_a, teacher_b = teacher_a.contiguous(), teacher_b.contiguous()
-                    mixed_teacher = torch.empty_like(teacher_a)
+                    if teacher_a.shape != teacher_b.shape or teacher_a.shape[:2] != (n, c):
+                        raise ValueError("teacher predictions must both be [N, num_classes, h, w]")
+                    if teacher_a.shape[2:] != (h, w):
+                        # row N2: low-resolution teacher logits (train.py:71-75) are up-sampled inside the mix
+                        d.teacher_h, d.teacher_w = teacher_a.shape[2], teacher_a.shape[3]
+                    mixed_teacher = torch.empty((n, c, h, w), dtype=torch.float32, device=dev)
                     d.teacher_a, d.teacher_b, d.mixed_teacher = teacher_a.data_ptr(), teacher_b.data_ptr(), mixed_teacher.data_ptr()
                     out["mixed_teacher"] = mixed_teacher
                 if not self.serial:

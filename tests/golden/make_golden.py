@@ -234,6 +234,35 @@ def consistency_case():
     save("consistency", **out)
 
 
+def upsample_case():
+    """Row N2: the interpolate calls of train.py:72-75 (teacher predictions to image size) followed by the
+    reference's mix (train.py:82)."""
+    # ATen's CPU bilinear kernel is not a single function of its input: with ONE intra-op thread and a
+    # batched input it takes a differently associated loop (results differ by up to 4 ulp) [probed].
+    # The goldens are made with the multi-threaded path, whose arithmetic is the documented formula
+    # (and the CUDA kernel's); "_1t" stores the single-thread variant for the tolerance check.
+    gen = torch.Generator().manual_seed(91)
+    out = {}
+    torch.set_num_threads(8)
+    for tag, (n, c, h, w, H, W) in {"x4": (2, 3, 16, 24, 64, 96), "x1": (1, 2, 20, 28, 20, 28),
+                                     "ragged": (2, 2, 13, 17, 50, 61), "x2": (1, 19, 8, 16, 16, 32)}.items():
+        a = torch.randn(n, c, h, w, generator=gen) * 3
+        b = torch.randn(n, c, h, w, generator=gen) * 3
+        mask = (torch.rand(n, 1, H, W, generator=gen) > 0.5).float()
+        ua = torch.nn.functional.interpolate(a, (H, W), mode='bilinear', align_corners=False)
+        ub = torch.nn.functional.interpolate(b, (H, W), mode='bilinear', align_corners=False)
+        out[f"{tag}_a"], out[f"{tag}_b"], out[f"{tag}_mask_bits"] = a.numpy(), b.numpy(), np.packbits(mask.numpy().astype(np.uint8))
+        out[f"{tag}_size"] = np.array([H, W])
+        out[f"{tag}_up_a"] = ua.numpy()
+        out[f"{tag}_mixed"] = ref_cowmix.mix_with_mask(ua, ub, mask).numpy()
+        if tag == "x4":
+            torch.set_num_threads(1)
+            out["x4_up_a_1t"] = torch.nn.functional.interpolate(a, (H, W), mode='bilinear', align_corners=False).numpy()
+            torch.set_num_threads(8)
+    torch.set_num_threads(1)
+    save("upsample", **out)
+
+
 def sgd_case():
     """Row N4: train.py:121-130 -- clip_grad_norm_ -> SGD.step() -> zero_grad() -> update_ema_variables,
     executed with torch's own optimizer / clip function and the reference's EMA function."""

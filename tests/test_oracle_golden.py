@@ -262,3 +262,39 @@ def test_sgd_ema_oracle_matches_torch_bit_for_bit(name):
         assert np.array_equal(ema[i].view(np.uint32), g[f"{name}_s2_ema{i}"].view(np.uint32)), (name, i)
         if moms is not None:
             assert np.array_equal(moms[i].view(np.uint32), g[f"{name}_s2_mom{i}"].view(np.uint32)), (name, i)
+
+
+# ------------------------------------------------------------------------------------------------
+# Row N2: bilinear up-sampling (train.py:72-75) + mix (train.py:82), golden = F.interpolate + the
+# reference's mix_with_mask
+# ------------------------------------------------------------------------------------------------
+UPSAMPLE_TAGS = ["x4", "x1", "ragged", "x2"]
+UPSAMPLE_BIT_EXACT = {"x4", "x1", "x2"}      # goldens produced by ATen's multi-threaded loop (see make_golden.py)
+
+
+def unpack_bits(bits, shape):
+    n = int(np.prod(shape))
+    return np.unpackbits(bits)[:n].reshape(shape).astype(np.float32)
+
+
+@pytest.mark.parametrize("tag", UPSAMPLE_TAGS)
+def test_upsample_oracle_matches_aten_bit_for_bit(tag):
+    g = load_golden("upsample")
+    a, b = g[f"{tag}_a"], g[f"{tag}_b"]
+    H, W = (int(v) for v in g[f"{tag}_size"])
+    ua = oracle.upsample_bilinear(a, (H, W))
+    mask = unpack_bits(g[f"{tag}_mask_bits"], (a.shape[0], 1, H, W))
+    mixed = oracle.mix(ua, oracle.upsample_bilinear(b, (H, W)), mask)
+    if tag in UPSAMPLE_BIT_EXACT:
+        assert np.array_equal(ua.view(np.uint32), g[f"{tag}_up_a"].view(np.uint32))
+        assert np.array_equal(mixed.view(np.uint32), g[f"{tag}_mixed"].view(np.uint32))
+    else:
+        # small planes stay below ATen's parallel grain and run its single-thread loop, which associates
+        # the same weights differently (<= 4 ulp); the bar there is north_star's 1e-5
+        tol = 1e-5 * float(np.abs(a).max())
+        assert np.allclose(ua, g[f"{tag}_up_a"], rtol=1e-5, atol=tol)
+        assert np.allclose(mixed, g[f"{tag}_mixed"], rtol=1e-5, atol=tol)
+    if tag == "x4":
+        # ATen's single-thread CPU loop associates differently (<= 4 ulp): inside north_star's 1e-5 bar
+        assert np.allclose(ua, g["x4_up_a_1t"], rtol=1e-5, atol=1e-5 * float(np.abs(a).max()))
+        assert not np.array_equal(ua, g["x4_up_a_1t"])
