@@ -27,79 +27,9 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "peer_device.cuh"
 
 namespace b200ssl {
-
-constexpr int kPeerMaxRanks = B200SSL_PEER_MAX_RANKS;
-constexpr int kPeerDepth = 4;
-constexpr int kPeerMaxWords = B200SSL_PEER_MAX_WORDS;
-constexpr int kPeerMaxFloats = B200SSL_PEER_MAX_FLOATS;
-constexpr size_t kAckOffset = (size_t)kPeerDepth * kPeerMaxRanks * kPeerMaxWords;  // in 8-byte words
-constexpr size_t kStatusOffset = kAckOffset + kPeerMaxRanks;
-constexpr size_t kMailWords = kStatusOffset + 16;
-
-struct PeerDev {  // by-value kernel parameter
-  unsigned long long* mail[kPeerMaxRanks];
-  int rank, world;
-  unsigned seq;
-  unsigned long long timeout_ns;
-};
-
-struct PeerFloats {
-  const float* p[kPeerMaxFloats];
-};
-
-__host__ __device__ inline size_t ll_index(int slot, int src, int w) {
-  return ((size_t)slot * kPeerMaxRanks + src) * kPeerMaxWords + w;
-}
-
-__device__ __forceinline__ unsigned long long ld_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
-// Block-cooperative: every thread of the (single) block calls it.
-__device__ void peer_post_block(const PeerDev& c, const long long* __restrict__ ints, int n_ints,
-                                const PeerFloats& f, int n_floats) {
-  unsigned long long* me = c.mail[c.rank];
-  // flow control: the slot of step seq was last used by step seq-depth
-  if ((int)threadIdx.x < c.world && c.seq > (unsigned)kPeerDepth) {
-    const unsigned need = c.seq - (unsigned)kPeerDepth;
-    const unsigned long long* a = me + kAckOffset + threadIdx.x;
-    const unsigned long long t0 = global_ns();
-    while ((int)((unsigned)ld_sys(a) - need) < 0) {
-      if (global_ns() - t0 > c.timeout_ns) {
-        atomicExch(me + kStatusOffset, 1ull);
-        break;
-      }
-      __nanosleep(200);
-    }
-  }
-  __syncthreads();
-  const int slot = (int)(c.seq % (unsigned)kPeerDepth);
-  const int nw = 2 * n_ints + n_floats;
-  for (int w = threadIdx.x; w < nw; w += blockDim.x) {
-    unsigned data;
-    if (w < 2 * n_ints) {
-      const unsigned long long v = (unsigned long long)ints[w >> 1];
-      data = (w & 1) ? (unsigned)(v >> 32) : (unsigned)v;
-    } else {
-      data = __float_as_uint(*f.p[w - 2 * n_ints]);
-    }
-    const unsigned long long word = ((unsigned long long)c.seq << 32) | data;
-    const size_t at = ll_index(slot, c.rank, w);
-    for (int r = 0; r < c.world; ++r) st_sys(c.mail[(c.rank + r) % c.world] + at, word);
-  }
-}
 
 __global__ void __launch_bounds__(256) peer_post_kernel(const __grid_constant__ PeerDev c,
                                                         const long long* __restrict__ ints, int n_ints,
@@ -179,6 +109,20 @@ static PeerDev device_view(const b200ssl_peer_comm* c, unsigned seq) {
   d.seq = seq;
   d.timeout_ns = c->timeout_ns;
   return d;
+}
+
+// used by step.cu when the producing kernel posts by itself: validates, advances the sequence number and
+// hands out the device view; the caller must make sure exactly one kernel calls peer_post_block with it
+int peer_begin_post(b200ssl_peer_comm* c, int n_ints, int n_floats, PeerDev* out) {
+  B200SSL_REQUIRE(c && c->connected && out, "peer_begin_post: communicator not connected");
+  B200SSL_REQUIRE(n_ints >= 0 && n_floats >= 0 && n_floats <= kPeerMaxFloats && 2 * n_ints + n_floats <= kPeerMaxWords &&
+                      n_ints + n_floats > 0, "peer_begin_post: payload does not fit");
+  B200SSL_REQUIRE(c->collected == c->seq, "peer_begin_post: the previous post has not been collected yet");
+  c->seq += 1;
+  c->n_ints = n_ints;
+  c->n_floats = n_floats;
+  *out = device_view(c, c->seq);
+  return 0;
 }
 
 // used by step.cu: the same post as b200ssl_peer_post (kept here so that a later fusion into the

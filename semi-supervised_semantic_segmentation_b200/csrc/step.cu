@@ -13,6 +13,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "peer_device.cuh"
 
 namespace b200ssl {
 
@@ -45,16 +46,23 @@ static SideStreams* side_streams() {
   return &ss;
 }
 
-int peer_post_impl(b200ssl_peer_comm* c, const long long* ints, int n_ints, const float* const* floats_host,
-                   int n_floats, cudaStream_t s);  // peer.cu
-
 }  // namespace b200ssl
+
+// the conditions under which b200ssl_binary_lovasz_fused takes the shape (it must not be asked to post
+// and then decline): mirrors the check at the top of binary_lovasz_fused_impl
+static bool fused_front_end_ok(const b200ssl_step_desc* d, int64_t hw) {
+  using namespace b200ssl;
+  return d->n > 0 && hw > 0 && d->classes >= 2 && d->classes <= 16 && hw % 4 == 0 && aligned16(d->scores) &&
+         aligned16(d->target) && (reinterpret_cast<uintptr_t>(d->labels_u8) & 3u) == 0 && d->labels_u8 && d->nonzero &&
+         d->grad && hw <= (1ll << 28) && d->n <= 65535;
+}
 
 static int loss_path_step_on(const b200ssl_step_desc* d, b200ssl_stream_t s_mix, b200ssl_stream_t s_lovasz,
                              b200ssl_stream_t s_ema) {
   using namespace b200ssl;
   const int64_t hw = (int64_t)d->h * d->w;
   int rc;
+  bool posted = false;
   b200ssl_stream_t stream = s_mix;
 
   // 1.+2. mask and mix.  With images present the threshold pass is fused into the mix: the field S
@@ -103,11 +111,23 @@ static int loss_path_step_on(const b200ssl_step_desc* d, b200ssl_stream_t s_mix,
       // losses.py:240: int_target = argmax(target, 1); :246 w_i = (tgt.sum() > 0)
       B200SSL_REQUIRE(d->labels_u8 && d->nonzero, "loss_path_step: binary mode needs labels_u8 / nonzero scratch");
       // fused front end: labels, weights, sort words and (when it uses the same labels) the matrix in one pass
-      rc = b200ssl_binary_lovasz_fused(d->scores, static_cast<const float*>(d->target), d->n, d->classes, hw, 1,
-                                       d->small + 2, d->labels_u8, d->nonzero, loss, d->small + 1, d->seg_loss,
-                                       d->seg_fg, d->seg_valid, d->grad, d->cm_labels ? nullptr : d->cm,
-                                       d->cm_has_ignore, d->cm_ignore_index, d->ws_lovasz, d->ws_lovasz_bytes,
-                                       stream);
+      // multi-GPU: when the matrix comes out of the same front end, the block that finalises the loss
+      // also posts [cm || loss] to the peers (one kernel computes and communicates)
+      PeerTail tail = {};
+      const bool fuse_post = d->peer && (!d->cm || !d->cm_labels) && fused_front_end_ok(d, hw);
+      if (fuse_post) {
+        rc = peer_begin_post(d->peer, d->cm ? d->classes * d->classes : 0, 1, &tail.dev);
+        if (rc) return rc;
+        tail.ints = d->cm;
+        tail.n_ints = d->cm ? d->classes * d->classes : 0;
+        tail.enabled = 1;
+      }
+      rc = binary_lovasz_fused_impl(d->scores, static_cast<const float*>(d->target), d->n, d->classes, hw, 1,
+                                    d->small + 2, d->labels_u8, d->nonzero, loss, d->small + 1, d->seg_loss,
+                                    d->seg_fg, d->seg_valid, d->grad, d->cm_labels ? nullptr : d->cm,
+                                    d->cm_has_ignore, d->cm_ignore_index, d->ws_lovasz, d->ws_lovasz_bytes,
+                                    stream, fuse_post ? &tail : nullptr);
+      if (fuse_post && rc == 0) posted = true;
       if (rc == 0) {
         done = true;
         if (d->cm && d->cm_labels) {
@@ -146,13 +166,15 @@ static int loss_path_step_on(const b200ssl_step_desc* d, b200ssl_stream_t s_mix,
       }
     }
   }
-  // 6. multi-GPU: post [cm || loss] into every rank's mailbox; the collect runs on the communicator's
-  // own stream, so this rank's streams never wait for a slower rank
+  // 6. multi-GPU: post [cm || loss] into every rank's mailbox (unless the last Lovasz pass already did);
+  // the collect runs on the communicator's own stream, so this rank's streams never wait for a slower rank
   if (d->peer) {
     B200SSL_REQUIRE(d->scores && d->small, "loss_path_step: the peer exchange needs the Lovasz stage");
-    const float* scalars[1] = {d->small};
-    rc = peer_post_impl(d->peer, d->cm, d->cm ? d->classes * d->classes : 0, scalars, 1, (cudaStream_t)s_lovasz);
-    if (rc) return rc;
+    if (!posted) {
+      const float* scalars[1] = {d->small};
+      rc = peer_post_impl(d->peer, d->cm, d->cm ? d->classes * d->classes : 0, scalars, 1, (cudaStream_t)s_lovasz);
+      if (rc) return rc;
+    }
     rc = b200ssl_peer_collect(d->peer, d->peer_cm_out, d->peer_loss_out, s_lovasz, nullptr);
     if (rc) return rc;
   }
