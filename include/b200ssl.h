@@ -295,6 +295,25 @@ int b200ssl_consistency_backward(const float* student, const float* teacher, int
                                  float* grad_student, b200ssl_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Row N3: lovasz_softmax straight from logits.  lovasz.py:155-160 expects F.softmax(logits, 1); the
+ * probabilities are never written here:
+ *   b200ssl_softmax_stats          per-pixel max_c x and sum_c exp(x - max)  ([n,hw] fp32 planes each)
+ *   b200ssl_lovasz_forward_logits  b200ssl_lovasz_forward with p = exp(x - max) / sum formed inside the
+ *                                  key-build; jgrad = unit gradients w.r.t. the PROBABILITIES (or the scaled
+ *                                  ones when grad_out != NULL, as b200ssl_lovasz_forward_backward)
+ *   b200ssl_softmax_backward       in place on the gradient buffer: dL/dz = (g - sum_c g_c p_c) * p
+ * --------------------------------------------------------------------------------------------- */
+int b200ssl_softmax_stats(const float* logits, int n, int c, int64_t hw, float* softmax_max, float* softmax_sum,
+                          b200ssl_stream_t stream);
+int b200ssl_lovasz_forward_logits(const b200ssl_lovasz_desc* d, const float* logits, const float* softmax_max,
+                                  const float* softmax_sum, const void* labels, const float* grad_out,
+                                  float* loss_out, float* seg_loss, int32_t* seg_fg, int32_t* seg_valid,
+                                  float* jgrad, void* workspace, size_t workspace_bytes,
+                                  b200ssl_stream_t stream);
+int b200ssl_softmax_backward(const float* logits, const float* softmax_max, const float* softmax_sum, float* grad,
+                             int n, int c, int64_t hw, b200ssl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Row N2: bilinear up-sampling (F.interpolate(..., mode='bilinear', align_corners=False), train.py:
  * 71-75,93-94, losses.py:18-19) fused into the mix.  b200ssl_mix2_upsampled is b200ssl_mix2 /
  * b200ssl_mix2_field with the SECOND tensor pair given at low resolution [n,c1,h_in,w_in]: the

@@ -160,6 +160,76 @@ def lovasz_softmax(probas, labels, classes='present', per_image=False, ignore=No
     return loss
 
 
+# --------------------------- row N3: lovasz_softmax straight from logits ------------------------
+class _LovaszFromLogits(torch.autograd.Function):
+    """logits -> lovasz_softmax(F.softmax(logits, 1), labels) without materialising the probabilities:
+    per-pixel (max, sum) statistics, probabilities formed inside the key-build, soft-max backward
+    applied in place on the gradient (b200ssl_softmax_stats / _lovasz_forward_logits / _softmax_backward)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, desc):
+        dev = logits.device
+        n, c = logits.shape[0], logits.shape[1]
+        hw = logits[0, 0].numel()
+        n_seg = lib.b200ssl_lovasz_num_segments(C.byref(desc))
+        if n_seg < 0:
+            check(n_seg, "lovasz_num_segments")
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        seg_loss = torch.empty(max(n_seg, 1), dtype=torch.float32, device=dev)
+        seg_meta = torch.empty((2, max(n_seg, 1)), dtype=torch.int32, device=dev)
+        stats = torch.empty((2, n, hw), dtype=torch.float32, device=dev)
+        jgrad = torch.empty_like(logits)
+        ws = _lib.workspaces.get(dev, "lovasz", lib.b200ssl_lovasz_workspace_bytes(C.byref(desc)))
+        with torch.cuda.device(dev):
+            st = stream_ptr(dev)
+            check(lib.b200ssl_softmax_stats(logits.data_ptr(), n, c, hw, stats[0].data_ptr(), stats[1].data_ptr(), st),
+                  "softmax_stats")
+            check(lib.b200ssl_lovasz_forward_logits(
+                C.byref(desc), logits.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), labels.data_ptr(), None,
+                loss.data_ptr(), seg_loss.data_ptr(), seg_meta[0].data_ptr(), seg_meta[1].data_ptr(),
+                jgrad.data_ptr(), ws.data_ptr(), ws.numel(), st), "lovasz_forward_logits")
+        ctx.desc, ctx.n_seg = desc, n_seg
+        ctx.save_for_backward(logits, stats, jgrad, seg_meta)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        logits, stats, jgrad, seg_meta = ctx.saved_tensors
+        dev = logits.device
+        desc, n_seg = ctx.desc, ctx.n_seg
+        n, c = logits.shape[0], logits.shape[1]
+        hw = logits[0, 0].numel()
+        with torch.cuda.device(dev):
+            st = stream_ptr(dev)
+            g_loss = g_loss.to(torch.float32).contiguous()
+            scale = torch.empty(max(n_seg, 1), dtype=torch.float32, device=dev)
+            check(lib.b200ssl_lovasz_seg_scale(C.byref(desc), g_loss.data_ptr(), seg_meta[0].data_ptr(),
+                                               seg_meta[1].data_ptr(), scale.data_ptr(), st), "lovasz_seg_scale")
+            grad = torch.empty_like(jgrad)
+            check(lib.b200ssl_lovasz_backward(C.byref(desc), scale.data_ptr(), jgrad.data_ptr(), grad.data_ptr(), st),
+                  "lovasz_backward")
+            check(lib.b200ssl_softmax_backward(logits.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
+                                               grad.data_ptr(), n, c, hw, st), "softmax_backward")
+        return grad, None, None
+
+
+def lovasz_softmax_with_logits(logits, labels, classes='present', per_image=False, ignore=None):
+    """`lovasz_softmax(F.softmax(logits, dim=1), labels, classes, per_image, ignore)` (lovasz.py:155-160's
+    contract: "probas ... typically the output of a softmax") computed from the logits; the gradient flows
+    to the logits.  Same degenerate-input behaviour as `lovasz_softmax`."""
+    logits, labels = _prepare(logits, labels)
+    if logits.shape[1] < 2:
+        raise ValueError("lovasz_softmax_with_logits needs at least 2 channels (use lovasz_softmax for sigmoid outputs)")
+    if not isinstance(classes, str) and len(classes) == 0:
+        return 0
+    if logits.shape[0] == 0 or logits[0, 0].numel() == 0:
+        if per_image and logits.shape[0] == 0:
+            return 0
+        return logits.permute(0, 2, 3, 1).reshape(-1, logits.shape[1]) * 0.
+    desc = _make_desc(logits, labels, classes, per_image, ignore)
+    return _LovaszFromLogits.apply(logits, labels, desc)
+
+
 # --------------------------- IoU helpers (lovasz.py:34-73), from the confusion matrix -----------
 def _mean(values, empty=0):
     values = list(values)

@@ -234,6 +234,25 @@ def consistency_case():
     save("consistency", **out)
 
 
+def softmax_lovasz_case():
+    """Row N3: lovasz_softmax(F.softmax(logits, 1), labels) with autograd, by the reference's own function."""
+    gen = torch.Generator().manual_seed(123)
+    out = {}
+    cases = {"c5_present": (2, 5, 24, 32, "present", False, None), "c21_all": (2, 21, 20, 20, "all", False, 255),
+             "c3_perimg": (3, 3, 16, 28, "present", True, 255), "c4_list": (2, 4, 18, 22, [0, 2], False, None)}
+    for tag, (n, c, h, w, classes, per_image, ignore) in cases.items():
+        logits = torch.randn(n, c, h, w, generator=gen) * 2.5
+        labels = coherent_labels(gen, n, c, h, w)
+        if ignore is not None:
+            labels[torch.rand(n, h, w, generator=gen) < 0.1] = ignore
+        x = logits.clone().requires_grad_(True)
+        loss = ref_lovasz.lovasz_softmax(torch.softmax(x, 1), labels, classes=classes, per_image=per_image, ignore=ignore)
+        loss.backward()
+        out[f"{tag}_logits"], out[f"{tag}_labels"] = logits.numpy(), labels.numpy()
+        out[f"{tag}_loss"], out[f"{tag}_grad"] = loss.detach().numpy(), x.grad.numpy()
+    save("softmax_lovasz", **out)
+
+
 def upsample_case():
     """Row N2: the interpolate calls of train.py:72-75 (teacher predictions to image size) followed by the
     reference's mix (train.py:82)."""

@@ -298,3 +298,26 @@ def test_upsample_oracle_matches_aten_bit_for_bit(tag):
         # ATen's single-thread CPU loop associates differently (<= 4 ulp): inside north_star's 1e-5 bar
         assert np.allclose(ua, g["x4_up_a_1t"], rtol=1e-5, atol=1e-5 * float(np.abs(a).max()))
         assert not np.array_equal(ua, g["x4_up_a_1t"])
+
+
+# ------------------------------------------------------------------------------------------------
+# Row N3: lovasz_softmax(F.softmax(logits, 1), labels), golden = the reference's function + autograd
+# ------------------------------------------------------------------------------------------------
+SOFTMAX_LOVASZ_CASES = {"c5_present": ("present", False, None), "c21_all": ("all", False, 255),
+                        "c3_perimg": ("present", True, 255), "c4_list": ([0, 2], False, None)}
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.mark.parametrize("tag", list(SOFTMAX_LOVASZ_CASES))
+def test_lovasz_from_logits_oracle_matches_reference(tag):
+    g = load_golden("softmax_lovasz")
+    classes, per_image, ignore = SOFTMAX_LOVASZ_CASES[tag]
+    loss, grad = oracle.lovasz_softmax_with_logits(g[f"{tag}_logits"], g[f"{tag}_labels"], classes=classes,
+                                                   per_image=per_image, ignore=ignore)
+    ref = float(g[f"{tag}_loss"])
+    assert abs(float(loss) - ref) <= 1e-5 * abs(ref)
+    assert rel_l2(grad, g[f"{tag}_grad"]) <= 1e-5
