@@ -51,7 +51,7 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(0)
     out = {"peak_GBps": PEAK}
 
-    only_optim = "--only-optim" in sys.argv
+    only_optim = "--only-optim" in sys.argv or "--only-new" in sys.argv
     # ---- configs[4]: 19-class confusion matrix over 1024x2048 masks, chunks of 32 masks (> L2)
     n, h, w, c = (1, 64, 64, 19) if only_optim else (32, 1024, 2048, 19)
     lab = coherent(n, c, h, w, gen)
@@ -93,7 +93,7 @@ def main():
 
     # ---- row N4: clip_grad_norm_ + SGD.step + zero_grad + EMA (train.py:122-130), fused vs torch's own
     # foreach CUDA path on the same GPU
-    for key in ["unet_mnv2_c2", "deeplabv3_r101_c21"]:
+    for key in ([] if "--only-new" in sys.argv else ["unet_mnv2_c2", "deeplabv3_r101_c21"]):
         shapes = bench.load_param_shapes(key)
         ps = [torch.nn.Parameter(torch.randn(s, device=dev, generator=gen)) for s in shapes]
         es = [torch.randn(s, device=dev, generator=gen) for s in shapes]
@@ -148,6 +148,47 @@ def main():
     bytes_ = 4 * (3 * 3 + 3 * c + 1) * n * h * w
     out[f"mix2_{n}x{c}x{h}x{w}"] = {"ms": round(ms, 4), "GBps": round(bytes_ / ms / 1e6, 1),
                                     "frac": round(bytes_ / ms / 1e6 / PEAK, 3)}
+    # ---- row N3: lovasz_softmax from logits, forward + backward, vs soft-max by torch + lovasz_softmax
+    for (n, c, h, w) in [(4, 21, 512, 512)]:
+        logits = torch.randn(n, c, h, w, device=dev, generator=gen) * 2
+        labels = coherent(n, c, h, w, gen)
+        labels[torch.rand(n, h, w, device=dev, generator=gen) < 0.03] = 255
+
+        def fused():
+            x = logits.detach().requires_grad_(True)
+            b200ssl.lovasz.lovasz_softmax_with_logits(x, labels, ignore=255).backward()
+
+        def unfused():
+            x = logits.detach().requires_grad_(True)
+            b200ssl.lovasz.lovasz_softmax(torch.softmax(x, 1), labels, ignore=255).backward()
+        ms_f = timeit(fused, reps=5, inner=4)
+        ms_u = timeit(unfused, reps=5, inner=4)
+        P = n * h * w
+        out[f"lovasz_from_logits_{n}x{c}x{h}x{w}"] = {"fused_ms": round(ms_f, 4), "torch_softmax_plus_lovasz_ms": round(ms_u, 4),
+                                                     "Mpix_s": round(P / ms_f / 1e3, 1), "gain": round(ms_u / ms_f, 3)}
+        del logits, labels
+
+    # ---- row N2: teacher logits at stride 4 up-sampled inside the mix vs F.interpolate x2 + mix
+    for (n, c, h, w) in [(16, 2, 512, 512), (8, 19, 512, 1024)]:
+        ia, ib = (torch.rand(n, 3, h, w, device=dev, generator=gen) for _ in range(2))
+        ta, tb = (torch.randn(n, c, h // 4, w // 4, device=dev, generator=gen) for _ in range(2))
+        mask = (torch.rand(n, 1, h, w, device=dev, generator=gen) > 0.5).float()
+        ms_f = timeit(lambda: b200ssl.cowmix.mix2_with_mask(ia, ib, ta, tb, mask))
+
+        def unfused():
+            ua = torch.nn.functional.interpolate(ta, (h, w), mode="bilinear", align_corners=False)
+            ub = torch.nn.functional.interpolate(tb, (h, w), mode="bilinear", align_corners=False)
+            b200ssl.cowmix.mix2_with_mask(ia, ib, ua, ub, mask)
+        ms_u = timeit(unfused)
+        bytes_ = (4 * (3 * 3 + c + 1) + 8 * c / 16) * n * h * w
+        out[f"mix2_upsampled_{n}x{c}x{h}x{w}"] = {"ms": round(ms_f, 4), "GBps": round(bytes_ / ms_f / 1e6, 1),
+                                                  "frac": round(bytes_ / ms_f / 1e6 / PEAK, 3),
+                                                  "interpolate_x2_plus_mix2_ms": round(ms_u, 4), "gain": round(ms_u / ms_f, 2)}
+        del ia, ib, ta, tb, mask
+    if "--only-new" in sys.argv:
+        print(json.dumps(out))
+        return
+
     # ---- the whole configs[1] step: this library vs the reference's ATen op sequence on the SAME GPU
     # (stock ATen/cub/cuDNN kernels; SURVEY 2.2: "the Blackwell kernel to beat").  oracle.torch_port is
     # test infrastructure; it is imported here only as the thing being compared against.
