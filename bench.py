@@ -369,9 +369,16 @@ def run_b200(args, rank, world, local_rank):
     top = max((k for k in ktimes if k in abytes), key=lambda k: ktimes[k][1])
     top_avg_ms = ktimes[top][1] / ktimes[top][0]
     achieved = abytes[top] / 1e9 / (top_avg_ms * 1e-3)
-    K_taps = None
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
+    # workload (profiles/traffic.json: kernel -> {bytes, source}); not measured live (never under a profiler)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(top, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
     roof = {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+            "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
             "avg_launch_ms": round(top_avg_ms, 5),
             "share_of_kernel_time": round(ktimes[top][1] / prof_steps / per_step_kernel_ms, 4),
             "stages": stages,
