@@ -120,9 +120,68 @@ softmax_backward_kernel(const float* __restrict__ x, const float* __restrict__ s
   }
 }
 
+// ---- register-resident variants for C <= 32: every logit (and gradient) of a pixel is read from memory
+//      exactly once (the generic kernels above sweep the channels twice, and the second sweep misses L2
+//      once the planes in flight exceed it: 20C instead of 12C bytes per pixel in the backward pass).
+//      One pixel per thread; a warp reads 128 contiguous bytes of every channel plane.
+constexpr int kSmRegC = 32;
+
+__global__ void __launch_bounds__(kSmThreads)
+softmax_stats_reg_kernel(const float* __restrict__ x, int n, int C, long long hw, float* __restrict__ smax,
+                         float* __restrict__ ssum) {
+  const long long total = (long long)n * hw;
+  for (long long q = (long long)blockIdx.x * kSmThreads + threadIdx.x; q < total; q += (long long)gridDim.x * kSmThreads) {
+    const long long img = q / hw;
+    const long long off = q - img * hw;
+    const float* base = x + img * C * hw + off;
+    float v[kSmRegC];
+#pragma unroll
+    for (int c = 0; c < kSmRegC; ++c) v[c] = (c < C) ? ld_stream_f1(base + (long long)c * hw) : -INFINITY;
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < kSmRegC; ++c)
+      if (c < C) m = (v[c] > m || v[c] != v[c]) ? v[c] : m;
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < kSmRegC; ++c)
+      if (c < C) s = __fadd_rn(s, expf(__fsub_rn(v[c], m)));
+    smax[q] = m;
+    ssum[q] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kSmThreads)
+softmax_backward_reg_kernel(const float* __restrict__ x, const float* __restrict__ smax, const float* __restrict__ ssum,
+                            float* grad, int n, int C, long long hw) {
+  const long long total = (long long)n * hw;
+  for (long long q = (long long)blockIdx.x * kSmThreads + threadIdx.x; q < total; q += (long long)gridDim.x * kSmThreads) {
+    const long long img = q / hw;
+    const long long off = q - img * hw;
+    const float* xb = x + img * C * hw + off;
+    float* gb = grad + img * C * hw + off;
+    const float m = __ldg(smax + q), s = __ldg(ssum + q);
+    float pr[kSmRegC], g[kSmRegC];
+#pragma unroll
+    for (int c = 0; c < kSmRegC; ++c) {
+      pr[c] = (c < C) ? ld_stream_f1(xb + (long long)c * hw) : 0.f;
+      g[c] = (c < C) ? gb[(long long)c * hw] : 0.f;
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < kSmRegC; ++c)
+      if (c < C) {
+        pr[c] = __fdiv_rn(expf(__fsub_rn(pr[c], m)), s);
+        dot = __fadd_rn(dot, __fmul_rn(g[c], pr[c]));
+      }
+#pragma unroll
+    for (int c = 0; c < kSmRegC; ++c)
+      if (c < C) gb[(long long)c * hw] = __fmul_rn(__fsub_rn(g[c], dot), pr[c]);
+  }
+}
+
 static int sm_grid(long long work) {
   long long blocks = (work + kSmThreads - 1) / kSmThreads;
-  const long long cap = (long long)kNumSMs * 8 * 8;
+  const long long cap = (long long)kNumSMs * 8 * 16;
   return (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
 }
 
@@ -139,7 +198,8 @@ int b200ssl_softmax_stats(const float* logits, int n, int c, int64_t hw, float* 
   const bool vec = (hw % 4 == 0) && aligned16(logits) && aligned16(softmax_max) && aligned16(softmax_sum);
   cudaStream_t s = (cudaStream_t)stream;
   prof_begin("softmax_stats", s);
-  if (vec) softmax_stats_kernel<4><<<sm_grid((long long)n * hw / 4), kSmThreads, 0, s>>>(logits, n, c, hw, softmax_max, softmax_sum);
+  if (c <= kSmRegC) softmax_stats_reg_kernel<<<sm_grid((long long)n * hw), kSmThreads, 0, s>>>(logits, n, c, hw, softmax_max, softmax_sum);
+  else if (vec) softmax_stats_kernel<4><<<sm_grid((long long)n * hw / 4), kSmThreads, 0, s>>>(logits, n, c, hw, softmax_max, softmax_sum);
   else softmax_stats_kernel<1><<<sm_grid((long long)n * hw), kSmThreads, 0, s>>>(logits, n, c, hw, softmax_max, softmax_sum);
   return check_launch("softmax_stats");
 }
@@ -153,7 +213,8 @@ int b200ssl_softmax_backward(const float* logits, const float* softmax_max, cons
   const bool vec = (hw % 4 == 0) && aligned16(logits) && aligned16(softmax_max) && aligned16(softmax_sum) && aligned16(grad);
   cudaStream_t s = (cudaStream_t)stream;
   prof_begin("softmax_backward", s);
-  if (vec) softmax_backward_kernel<4><<<sm_grid((long long)n * hw / 4), kSmThreads, 0, s>>>(logits, softmax_max, softmax_sum, grad, n, c, hw);
+  if (c <= kSmRegC) softmax_backward_reg_kernel<<<sm_grid((long long)n * hw), kSmThreads, 0, s>>>(logits, softmax_max, softmax_sum, grad, n, c, hw);
+  else if (vec) softmax_backward_kernel<4><<<sm_grid((long long)n * hw / 4), kSmThreads, 0, s>>>(logits, softmax_max, softmax_sum, grad, n, c, hw);
   else softmax_backward_kernel<1><<<sm_grid((long long)n * hw), kSmThreads, 0, s>>>(logits, softmax_max, softmax_sum, grad, n, c, hw);
   return check_launch("softmax_backward");
 }

@@ -64,7 +64,7 @@ def test_softmax_stats_and_backward_kernels(ssl):
     from b200ssl import _lib
     dev = torch.device("cuda:0")
     gen = torch.Generator().manual_seed(4)
-    for (n, c, h, w) in [(2, 21, 32, 48), (1, 3, 17, 19)]:
+    for (n, c, h, w) in [(2, 21, 32, 48), (1, 3, 17, 19), (1, 36, 24, 24), (2, 33, 9, 7)]:
         x = (torch.randn(n, c, h, w, generator=gen) * 4).to(dev)
         hw = h * w
         stats = torch.empty((2, n, hw), device=dev)
