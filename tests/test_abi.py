@@ -138,3 +138,31 @@ def test_product_path_refuses_cpu_tensors_and_never_touches_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
                 assert "liboracle" not in src, f
+
+
+def test_optim_and_peer_refuse_cpu_and_bad_arguments():
+    """Rows N4 / 8e host logic without a GPU: constructor validation mirrors torch.optim.SGD, CPU tensors
+    are refused (no fallback), and a peer exchange that cannot fit its mailbox row is rejected up front."""
+    import torch
+    import b200ssl
+    p = torch.nn.Parameter(torch.zeros(4))
+    with pytest.raises(ValueError):
+        b200ssl.optim.FusedSGD([p], lr=-1.0)
+    with pytest.raises(ValueError):
+        b200ssl.optim.FusedSGD([p], lr=0.1, momentum=0.0, nesterov=True)
+    opt = b200ssl.optim.FusedSGD([p], lr=0.1, momentum=0.9)
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError):
+        opt.step()
+    with pytest.raises(RuntimeError):
+        b200ssl.optim.clip_grad_norm_([p], 1.0)
+    with pytest.raises(NotImplementedError):
+        b200ssl.optim.clip_grad_norm_([p], 1.0, norm_type=1.0)
+    with pytest.raises(ValueError):
+        b200ssl.utils.PeerAllReduce(3000, 1, "cuda:0")          # 2*3000+1 words > one mailbox row
+    with pytest.raises(ValueError):
+        b200ssl.utils.StepReducer(2, 1, torch.device("cpu"), backend="nvlink")
+    with pytest.raises(RuntimeError):
+        b200ssl.cowmix.upsample_bilinear(torch.zeros(1, 1, 4, 4), (8, 8))
+    with pytest.raises(RuntimeError):
+        b200ssl.lovasz.lovasz_softmax_with_logits(torch.zeros(1, 3, 4, 4), torch.zeros(1, 4, 4, dtype=torch.int64))
