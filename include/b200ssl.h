@@ -487,6 +487,9 @@ typedef struct b200ssl_step_desc {
   /* row N2: teacher_a / teacher_b are [n,classes,teacher_h,teacher_w] and are bilinearly up-sampled to
    * h x w inside the mix (0 = they are already h x w) */
   int32_t teacher_h, teacher_w;
+  /* upstream gradient of the loss (device scalar); NULL = small[2].  A caller that keeps a constant 1.0 on
+   * the device passes it here and then `small` needs no initialisation at all. */
+  const float* grad_out;
 } b200ssl_step_desc;
 
 int b200ssl_loss_path_step(const b200ssl_step_desc* d, b200ssl_stream_t stream);

@@ -65,7 +65,8 @@ class StepDesc(C.Structure):
         [("ws_cowmix", C.c_void_p), ("ws_cowmix_bytes", C.c_size_t), ("ws_lovasz", C.c_void_p),
          ("ws_lovasz_bytes", C.c_size_t), ("ema_table", C.c_void_p), ("ema_entries", C.c_int64),
          ("ema_alpha", C.c_double), ("peer", C.c_void_p), ("peer_cm_out", C.c_void_p),
-         ("peer_loss_out", C.c_void_p), ("teacher_h", C.c_int32), ("teacher_w", C.c_int32)])
+         ("peer_loss_out", C.c_void_p), ("teacher_h", C.c_int32), ("teacher_w", C.c_int32),
+         ("grad_out", C.c_void_p)])
 
 
 # name -> (restype, argtypes); mirrors include/b200ssl.h one to one

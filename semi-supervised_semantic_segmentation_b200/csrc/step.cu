@@ -105,7 +105,8 @@ static int loss_path_step_on(const b200ssl_step_desc* d, b200ssl_stream_t s_mix,
   // 3. Lovasz forward + backward with the upstream gradient small[2], 5. confusion matrix
   stream = s_lovasz;
   if (d->scores) {
-    float* loss = d->small;        // [0] loss  [1] denom  [2] upstream gradient (1.0)
+    float* loss = d->small;        // [0] loss  [1] denom  [2] upstream gradient (1.0) unless d->grad_out is given
+    const float* grad_out = d->grad_out ? d->grad_out : d->small + 2;
     bool done = false;
     if (d->mode == B200SSL_STEP_BINARY) {
       // losses.py:240: int_target = argmax(target, 1); :246 w_i = (tgt.sum() > 0)
@@ -123,7 +124,7 @@ static int loss_path_step_on(const b200ssl_step_desc* d, b200ssl_stream_t s_mix,
         tail.enabled = 1;
       }
       rc = binary_lovasz_fused_impl(d->scores, static_cast<const float*>(d->target), d->n, d->classes, hw, 1,
-                                    d->small + 2, d->labels_u8, d->nonzero, loss, d->small + 1, d->seg_loss,
+                                    grad_out, d->labels_u8, d->nonzero, loss, d->small + 1, d->seg_loss,
                                     d->seg_fg, d->seg_valid, d->grad, d->cm_labels ? nullptr : d->cm,
                                     d->cm_has_ignore, d->cm_ignore_index, d->ws_lovasz, d->ws_lovasz_bytes,
                                     stream, fuse_post ? &tail : nullptr);
@@ -152,7 +153,7 @@ static int loss_path_step_on(const b200ssl_step_desc* d, b200ssl_stream_t s_mix,
         ld.class_mode = B200SSL_LOVASZ_LIST; ld.n_list = 1; ld.class_list[0] = 1;
         ld.has_ignore = 1; ld.ignore_index = 255; ld.label_dtype = B200SSL_U8;
       }
-      rc = b200ssl_lovasz_forward_backward(&ld, d->scores, labels, d->small + 2,
+      rc = b200ssl_lovasz_forward_backward(&ld, d->scores, labels, grad_out,
                                            d->mode == B200SSL_STEP_BINARY ? d->nonzero : nullptr, loss,
                                            d->small + 1, d->seg_loss, d->seg_fg, d->seg_valid, d->grad,
                                            d->ws_lovasz, d->ws_lovasz_bytes, stream);

@@ -43,7 +43,7 @@ class LossPathStep:
         self._ema = mean_teacher.EmaUpdater()
         self._scratch_key = None
         self._scratch = None
-        self._small_init = None
+        self._one = None
         self._bound = None          # (params list, ema list, table pointer, entries)
         self._desc_key = None
         self._desc = None
@@ -71,7 +71,7 @@ class LossPathStep:
                 "ws_c": torch.empty(max(ws_c, 256), dtype=torch.uint8, device=dev),
                 "ws_l": torch.empty(max(ws_l, 256), dtype=torch.uint8, device=dev),
             }
-            self._small_init = torch.tensor([0.0, 0.0, 1.0, 0.0], dtype=torch.float32, device=dev)
+            self._one = torch.ones(1, dtype=torch.float32, device=dev)     # constant upstream gradient
             self._scratch_key = key
         return self._scratch
 
@@ -135,13 +135,14 @@ class LossPathStep:
             ns = max(n_seg, 1)
             out = {}
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            current = torch.cuda.current_device() == dev.index     # the library launches on the current device
             # Everything the Lovasz / matrix / EMA chains touch is allocated and initialised FIRST, so
             # that the fork point can be recorded before the mask parameters and the noise are produced.
             # ---- Lovasz
-            small = self._small_init.clone()
+            small = torch.empty(4, dtype=torch.float32, device=dev)    # [loss, denom, -, -]: written by the step
             grad = torch.empty_like(scores)
             d.scores, d.target = scores.data_ptr(), target.data_ptr()
-            d.grad, d.small = grad.data_ptr(), small.data_ptr()
+            d.grad, d.small, d.grad_out = grad.data_ptr(), small.data_ptr(), self._one.data_ptr()
             d.seg_loss = sc["segf"].data_ptr()
             d.seg_fg, d.seg_valid = sc["segi"].data_ptr(), sc["segi"].data_ptr() + 4 * ns
             d.nonzero = sc["segi"].data_ptr() + 8 * ns
@@ -189,8 +190,11 @@ class LossPathStep:
                     out["mixed_teacher"] = mixed_teacher
                 if not self.serial:
                     # fork point: the Lovasz / EMA chains need neither the mask parameters nor the noise
-                    with torch.cuda.device(dev):
+                    if current:
                         check(lib.b200ssl_loss_path_fork(stream), "loss_path_fork")
+                    else:
+                        with torch.cuda.device(dev):
+                            check(lib.b200ssl_loss_path_fork(stream), "loss_path_fork")
                     d.flags |= _lib.STEP_PREFORKED
                 p, sigmas = cowmix.draw_mask_parameters(n, self.mask_proportion_range, self.sigma_range)
                 size, taps_dev = cowmix.upload_mask_parameters(p, sigmas, dev)
@@ -207,8 +211,10 @@ class LossPathStep:
                 cm_sum, loss_sum = self.peer.next_outputs()
                 d.peer, d.peer_cm_out, d.peer_loss_out = self.peer.handle, cm_sum.data_ptr(), loss_sum.data_ptr()
                 out["cm_sum"], out["loss_sum"] = cm_sum.view(c, c), loss_sum[0]
-            with torch.cuda.device(dev):
-                check(lib.b200ssl_loss_path_step(C.byref(d), stream),
-                      "loss_path_step")
+            if current:
+                check(lib.b200ssl_loss_path_step(C.byref(d), stream), "loss_path_step")
+            else:
+                with torch.cuda.device(dev):
+                    check(lib.b200ssl_loss_path_step(C.byref(d), stream), "loss_path_step")
             out["loss"], out["grad"], out["labels"] = small[0], grad, labels
             return out
