@@ -89,7 +89,7 @@ def test_lovasz_full_size_properties(ssl, n, c, h, w, from_logits):
 def test_ema_and_sgd_full_parameter_sets(ssl, key):
     dev = torch.device("cuda:0")
     with open(os.path.join(ROOT, "tests", "golden", "param_shapes.json")) as f:
-        shapes = json.load(f)[key]
+        shapes = json.load(f)[key]["shapes"]
     gen = torch.Generator(device=dev).manual_seed(7)
     ps = [torch.nn.Parameter(torch.randn(s, device=dev, generator=gen)) for s in shapes]
     es = [torch.randn(s, device=dev, generator=gen) for s in shapes]
