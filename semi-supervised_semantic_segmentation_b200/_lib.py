@@ -209,18 +209,26 @@ def label_dtype_code(t):
 
 
 class WorkspaceCache:
-    """One growing scratch tensor per (device, tag); allocation is PyTorch's (caching allocator),
-    the library itself never allocates."""
+    """One growing scratch tensor per (device, CUDA stream, tag); allocation is PyTorch's (caching
+    allocator), the library itself never allocates.  A scratch buffer holds keys, status words and tickets
+    of the kernels in flight, so it is only ever shared between launches that are ordered on ONE stream:
+    calls issued on different streams get different buffers.  When a buffer is replaced by a larger one
+    the old tensor is `record_stream`ed on the stream whose kernels may still be using it before the
+    reference is dropped, so the allocator cannot hand it out while they run."""
 
     def __init__(self):
         self._bufs = {}
 
     def get(self, device, tag, nbytes):
         import torch
-        key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        stream = torch.cuda.current_stream(index)
+        key = (index, stream.cuda_stream, tag)
         buf = self._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
-            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            if buf is not None:
+                buf.record_stream(stream)
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=torch.device("cuda", index))
             self._bufs[key] = buf
         return buf
 

@@ -40,6 +40,15 @@ inline int check_launch(const char* what) {
     }                                   \
   } while (0)
 
+// per-device caches (function attributes, side streams) are indexed by this; devices beyond the table
+// share the last slot, which callers never cache
+constexpr int kMaxDevices = 65;
+inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices - 1) return kMaxDevices - 1;
+  return dev;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

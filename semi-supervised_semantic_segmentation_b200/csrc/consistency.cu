@@ -106,7 +106,8 @@ consistency_grad_kernel(const float* __restrict__ student, const float* __restri
     const long long i0 = q * 4;
     const bool full = vec && (i0 + 4 <= hw);
     // pass 1 over the channels: confidence of the 4 pixels (teacher only)
-    float tmax[4] = {-1.f, -1.f, -1.f, -1.f};
+    // (raw logits here, so the sentinel is -inf: the forward kernel's -1 is only safe for sigmoid values)
+    float tmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     for (int c = 0; c < C; ++c) {
       if (full) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(tp + (long long)c * hw + i0));

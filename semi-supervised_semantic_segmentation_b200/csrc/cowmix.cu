@@ -447,11 +447,14 @@ static int launch_conv_tma(const float* in, float* out, const float* taps, int K
   const int n_boxes = ((kTileWarps - 1) * kConvR + groups * kConvR + kBoxRows - 1) / kBoxRows;
   const size_t smem = (size_t)kTileHeadBytes + (((size_t)(K + 3 * kConvR) * 8 + 127) / 128) * 128 + (size_t)n_boxes * kBoxBytes;
   auto kern = conv_tma_tile_kernel<STATS>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(kTileHeadBytes + (((193 + 3 * kConvR) * 8 + 127) / 128) * 128 + kMaxBoxes * kBoxBytes));
-    attr_done = true;
+  // the opt-in shared-memory limit is a per-DEVICE attribute of the function
+  static bool attr_done[kMaxDevices] = {};
+  const int dev = current_device_slot();
+  if (!attr_done[dev]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(kTileHeadBytes + (((193 + 3 * kConvR) * 8 + 127) / 128) * 128 + kMaxBoxes * kBoxBytes)) ==
+        cudaSuccess)
+      attr_done[dev] = dev != kMaxDevices - 1;
   }
   const ConvGrid g = conv_tma_grid(n, A, B);
   prof_begin(name, s);

@@ -182,7 +182,9 @@ grad_norm_final_kernel(const double* __restrict__ partials, long long n_entries,
     // clip_coef = max_norm / (total_norm + 1e-6): python float / tensor = reciprocal(tensor) * float
     const float coef = __fmul_rn(__frcp_rn(__fadd_rn(norm, 1e-6f)), max_norm);
     out[0] = norm;
-    out[1] = fminf(coef, 1.0f);  // torch.clamp(clip_coef, max=1.0); NaN stays NaN like torch
+    // torch.clamp(clip_coef, max=1.0) propagates NaN (and so poisons every gradient, like torch); fminf would
+    // return 1.0 for a NaN coefficient
+    out[1] = (coef != coef) ? coef : fminf(coef, 1.0f);
   }
 }
 

@@ -13,8 +13,10 @@ and `step()` takes the two neighbours of the optimiser step as options:
                           zero_grad=True)
 
 is one reduction + one update launch for all tensors (28-32 B per parameter) instead of ~7 element-wise
-passes per tensor.  `clip_grad_norm_` is the stand-alone mirror of the torch function.  Arithmetic is
-torch's op for op (csrc/optim.cu); no CPU fallback.
+passes per tensor.  `clip_grad_norm_` is the stand-alone mirror of the torch function.  The update
+arithmetic is torch's op for op (csrc/optim.cu: bit-exact given the same clip coefficient); the total norm
+is an fp64 sum of squares in a fixed order, within 1e-6 relative of torch's fp32 norm-of-norms (whose
+reduction order is unspecified), so the coefficient can differ from torch's in the last bit.  No CPU fallback.
 """
 import ctypes as C
 
@@ -138,6 +140,19 @@ class FusedSGD(torch.optim.Optimizer):
         self._tables = [_SgdTable() for _ in self.param_groups]
         self._norm_table = _SgdTable()
         self._cache = {}
+        self._frozen_ema = None
+
+    # the cached tensor lists point at state[p]["momentum_buffer"] objects: anything that replaces the
+    # state or the groups invalidates them
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._cache = {}
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)
+        if hasattr(self, "_tables"):
+            self._tables.append(_SgdTable())
+            self._cache = {}
 
     @torch.no_grad()
     def step(self, closure=None, max_grad_norm=None, ema_params=None, ema_alpha=None, zero_grad=False):
@@ -165,7 +180,7 @@ class FusedSGD(torch.optim.Optimizer):
             if cache is None or cache["with_grad"] != with_grad or cache["ema_key"] != ema_key or \
                     cache["n"] != len(gparams):
                 params = [p for p in gparams if p.grad is not None]
-                moms, first = None, False
+                moms, fresh = None, None
                 if group["momentum"] != 0 and params:
                     fresh = []
                     moms = []
@@ -177,9 +192,6 @@ class FusedSGD(torch.optim.Optimizer):
                         else:
                             fresh.append(False)
                         moms.append(st["momentum_buffer"])
-                    if any(fresh) and not all(fresh):
-                        raise RuntimeError("FusedSGD: parameters of one group must start receiving gradients together")
-                    first = all(fresh)
                 emas = None
                 if ema_params is not None:
                     if not isinstance(ema_params, (list, tuple)):
@@ -188,7 +200,17 @@ class FusedSGD(torch.optim.Optimizer):
                         raise ValueError("FusedSGD.step: ema_params must match the optimiser's parameters")
                     emas = [ema_params[offset + k] for k, p in enumerate(gparams) if p.grad is not None]
                 cache = self._cache[gi] = dict(with_grad=with_grad, ema_key=ema_key, n=len(gparams), params=params,
-                                               moms=moms, emas=emas, first=first)
+                                               moms=moms, emas=emas, first=bool(fresh) and all(fresh))
+                if fresh and any(fresh) and not all(fresh):
+                    # some tensors receive their first gradient later than the others (torch.optim.SGD
+                    # initialises each buffer on ITS first step): this one step runs as two sub-plans
+                    for flag in (True, False):
+                        idx = [k for k, f in enumerate(fresh) if f == flag]
+                        sub = dict(params=[params[k] for k in idx], moms=[moms[k] for k in idx],
+                                   emas=None if emas is None else [emas[k] for k in idx], first=flag)
+                        plan.append((group, _SgdTable(), sub))
+                    offset += len(gparams)
+                    continue
             else:
                 cache["first"] = False
             offset += len(gparams)
@@ -198,7 +220,7 @@ class FusedSGD(torch.optim.Optimizer):
         for group, tab, cache in plan:
             tab.prepare(cache["params"], [p.grad for p in cache["params"]], cache["moms"], cache["emas"])
         if max_grad_norm is not None and plan:
-            if single:
+            if single and len(plan) == 1:
                 norm_tab = plan[0][1]                       # the update table already lists every gradient
             else:
                 norm_tab = self._norm_table
@@ -216,4 +238,20 @@ class FusedSGD(torch.optim.Optimizer):
             with torch.cuda.device(tab.device):
                 check(lib.b200ssl_sgd_ema_multi(tab.table.data_ptr(), tab.entries, coef_ptr, C.byref(h),
                                                 stream_ptr(tab.device)), "sgd_ema_multi")
-        return total_norm if max_grad_norm is not None else loss
+        if ema_params is not None:
+            # parameters without a gradient (frozen) are not touched by SGD, but the reference's
+            # update_ema_variables (mean_teacher.py:10-11) still moves their teacher copy
+            every = [p for g in groups for p in g["params"]]
+            frozen = [k for k, p in enumerate(every) if p.grad is None]
+            if frozen:
+                from . import mean_teacher
+                key = (id(ema_params), tuple(frozen))
+                if self._frozen_ema is None or self._frozen_ema[0] != key:
+                    self._frozen_ema = (key, mean_teacher.EmaUpdater(), [ema_params[k] for k in frozen],
+                                        [every[k] for k in frozen])
+                _, upd, e_list, p_list = self._frozen_ema
+                upd(e_list, p_list, float(ema_alpha))
+        if max_grad_norm is not None:
+            # a copy: the persistent [norm, coefficient] buffer is overwritten by the next step
+            return total_norm.clone() if total_norm is not None else torch.tensor(0.0)
+        return loss

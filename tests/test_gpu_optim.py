@@ -113,3 +113,77 @@ def test_optim_refuses_cpu_tensors(ssl):
     p.grad = torch.ones(4)
     with pytest.raises(RuntimeError):
         ssl.optim.clip_grad_norm_([p], 1.0)
+
+
+def _twin(shapes, dev, gen):
+    a = [torch.nn.Parameter(torch.randn(s, generator=gen).to(dev)) for s in shapes]
+    b = [torch.nn.Parameter(p.detach().cpu().clone()) for p in a]      # torch.optim.SGD + reference EMA on the CPU
+    return a, b
+
+
+def _same(a, b):
+    return all(np.array_equal(u32(x.detach().cpu().numpy()), u32(y.detach().cpu().numpy())) for x, y in zip(a, b))
+
+
+def test_fused_sgd_lifecycle_like_torch(ssl):
+    """torch.optim.SGD behaviours the cached tensor lists must not break: a parameter whose first
+    gradient arrives later than the others, a frozen parameter whose teacher copy still moves
+    (mean_teacher.py:10-11), load_state_dict between steps, add_param_group, and a returned norm that
+    survives the next step.  Bit-exact against torch.optim.SGD + the reference's EMA (CPU, like the goldens)."""
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(21)
+    shapes = [(33,), (17, 5), (4100,), (3,)]
+    mine, ref = _twin(shapes, dev, gen)
+    ema = [torch.randn(s, generator=gen).to(dev) for s in shapes]
+    ema_ref = [e.cpu().clone() for e in ema]
+    kw = dict(lr=0.05, momentum=0.9, weight_decay=5e-4)
+    opt, opt_ref = ssl.optim.FusedSGD(mine, **kw), torch.optim.SGD(ref, **kw)
+    alpha = 0.99
+
+    def ref_ema():
+        for e, p in zip(ema_ref, ref):
+            e.mul_(alpha).add_(p.detach(), alpha=1 - alpha)
+
+    def give(idx):
+        for k in idx:
+            gr = torch.randn(shapes[k], generator=gen)
+            mine[k].grad, ref[k].grad = gr.to(dev), gr.clone()
+
+    # step 0: parameter 3 is frozen, parameter 2 has no gradient yet
+    give([0, 1])
+    opt.step(ema_params=ema, ema_alpha=alpha); opt_ref.step(); ref_ema()
+    assert _same(mine, ref) and _same(ema, ema_ref)
+    # step 1: parameter 2 receives its first gradient one step late (its buffer starts as a copy of it)
+    give([0, 1, 2])
+    opt.step(ema_params=ema, ema_alpha=alpha); opt_ref.step(); ref_ema()
+    assert _same(mine, ref) and _same(ema, ema_ref)
+    give([0, 1, 2])
+    opt.step(ema_params=ema, ema_alpha=alpha); opt_ref.step(); ref_ema()
+    assert _same(mine, ref) and _same(ema, ema_ref)
+    # load_state_dict: new momentum tensors must be the ones the next step uses
+    sd = opt_ref.state_dict()
+    for st in sd["state"].values():
+        st["momentum_buffer"] = st["momentum_buffer"] * 0.5
+    opt.load_state_dict(sd); opt_ref.load_state_dict(sd)
+    give([0, 1, 2])
+    n1 = opt.step(max_grad_norm=1e9, ema_params=ema, ema_alpha=alpha); opt_ref.step(); ref_ema()
+    assert _same(mine, ref) and _same(ema, ema_ref)
+    # add_param_group + the returned norm is a copy
+    extra, extra_ref = _twin([(9,)], dev, gen)
+    opt.add_param_group({"params": extra}); opt_ref.add_param_group({"params": extra_ref})
+    ema.append(torch.zeros(9, device=dev)); ema_ref.append(torch.zeros(9))
+    mine += extra; ref += extra_ref; shapes.append((9,))
+    give([0, 1, 2, 4])
+    kept = float(n1)
+    n2 = opt.step(max_grad_norm=1e9, ema_params=ema, ema_alpha=alpha); opt_ref.step(); ref_ema()
+    assert _same(mine, ref) and _same(ema, ema_ref)
+    assert float(n1) == kept and float(n2) != kept
+
+
+def test_clip_coefficient_nan_poisons_like_torch(ssl):
+    dev = torch.device("cuda:0")
+    ps = [torch.nn.Parameter(torch.zeros(8, device=dev)) for _ in range(2)]
+    ps[0].grad = torch.full((8,), float("nan"), device=dev)
+    ps[1].grad = torch.ones(8, device=dev)
+    tn = ssl.optim.clip_grad_norm_(ps, 1.0)
+    assert torch.isnan(tn) and torch.isnan(ps[1].grad).all()            # torch.clamp propagates NaN

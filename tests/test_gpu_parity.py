@@ -591,6 +591,26 @@ def test_consistency_vs_oracle(ssl, dev, n, c, h, w, thr):
     assert np.allclose(got, o_grad, rtol=1e-4, atol=1e-6 * float(np.abs(o_grad).max()))
 
 
+def test_consistency_low_threshold_negative_teacher(ssl, dev):
+    """Every teacher logit far below -1 and a threshold below sigmoid(-1): forward and backward must take
+    the same confidence decision (the gradient kernel maximises raw logits, the forward sigmoid values)."""
+    gen = torch.Generator().manual_seed(77)
+    n, c, h, w, thr = 2, 3, 40, 52, 0.1
+    student = torch.randn(n, c, h, w, generator=gen) * 2
+    teacher = -1.5 - torch.rand(n, c, h, w, generator=gen) * 4          # sigmoid in (0.004, 0.18)
+    teacher = _clear_of_threshold(teacher, thr)
+    x = student.to(dev).requires_grad_(True)
+    loss, conf = ssl.consistency.confidence_masked_consistency(x, teacher.to(dev), thr)
+    loss.backward()
+    o_loss, o_conf, o_grad = oracle.consistency_loss(student.numpy(), teacher.numpy(), thr)
+    assert 0.0 < float(o_conf) < 1.0                                    # both decisions occur
+    assert abs(float(loss) - float(o_loss)) <= REL * abs(float(o_loss))
+    assert abs(float(conf) - float(o_conf)) <= 1e-7
+    got = x.grad.cpu().numpy()
+    assert np.array_equal(got == 0, o_grad == 0)                        # masked pixels carry no gradient
+    assert np.linalg.norm(got - o_grad) <= REL * np.linalg.norm(o_grad)
+
+
 def test_consistency_no_confident_pixel_is_nan_like_the_reference(ssl, dev):
     student = torch.zeros(1, 2, 8, 8, device=dev)
     teacher = torch.zeros(1, 2, 8, 8, device=dev)              # sigmoid = 0.5 < 0.97 everywhere
