@@ -388,17 +388,21 @@ int b200ssl_sgd_ema_multi(const b200ssl_sgd_chunk* table_dev, int64_t n_entries,
  *                         rank order; exchanged by the caller, e.g. torch.distributed.all_gather).
  *   b200ssl_peer_connect_ptrs  the same for communicators living in ONE process (plain device
  *                         pointers from b200ssl_peer_mailbox; peer access must already be enabled).
- *   b200ssl_peer_post     stream-ordered, does not wait for anybody unless it is more than 3 steps
- *                         ahead of the slowest rank's collect.  floats_host: HOST array of n_floats
- *                         DEVICE pointers to fp32 scalars.
- *   b200ssl_peer_collect  sums into ints_out [n_ints] int64 / floats_out [n_floats] fp64.  stream != NULL:
- *                         runs there.  stream == NULL (lazy): runs on the communicator's own high-priority
- *                         stream, ordered after `post_stream`; the caller's streams never wait for a
- *                         slower rank until b200ssl_peer_join(comm, stream) orders `stream` after it.
- *   b200ssl_peer_allreduce  post + collect on `stream`.
+ *   b200ssl_peer_post     publishes the next step (stream-ordered; waits only if it is more than 3 steps
+ *                         ahead of the slowest rank's collect).  floats_host: HOST array of n_floats DEVICE
+ *                         pointers to fp32 scalars.  prev_ints_out / prev_floats_out (may be NULL): the same
+ *                         launch also completes the PREVIOUS step's exchange into them -- by then every
+ *                         peer posted it a whole step ago, so a steady-state step pays no separate collect.
+ *   b200ssl_peer_collect  sums the LATEST posted step into ints_out [n_ints] int64 / floats_out [n_floats]
+ *                         fp64 on `stream` (ordered after the post); does nothing if that step has already
+ *                         been collected (idempotent: the flush after the last step of a run).
+ *   b200ssl_peer_allreduce  post + collect of the same step in ONE launch on `stream`.
+ * Sequence numbers live in device memory: no call advances host state, so the calls are CUDA-graph
+ * capturable and a replayed graph exchanges a new step every time.  One payload shape per communicator.
  *   b200ssl_peer_status   (synchronous) B200SSL_ETIMEOUT if any wait gave up (default 20 s per wait,
  *                         env B200SSL_PEER_TIMEOUT_MS); results of such a step are undefined.
- * One exchange in flight per communicator; posts must be issued in the same order on all ranks.
+ * Posts must be issued in the same order on all ranks; every rank must collect (or fold-collect) at
+ * least every 4th step.
  * Destroy only after all ranks have finished (barrier first).
  * --------------------------------------------------------------------------------------------- */
 #define B200SSL_PEER_MAX_RANKS 16
@@ -412,10 +416,10 @@ void* b200ssl_peer_mailbox(b200ssl_peer_comm* comm);
 int b200ssl_peer_connect(b200ssl_peer_comm* comm, const unsigned char* handles);
 int b200ssl_peer_connect_ptrs(b200ssl_peer_comm* comm, void* const* mailboxes_host);
 int b200ssl_peer_post(b200ssl_peer_comm* comm, const long long* ints, int n_ints,
-                      const float* const* floats_host, int n_floats, b200ssl_stream_t stream);
+                      const float* const* floats_host, int n_floats, long long* prev_ints_out,
+                      double* prev_floats_out, b200ssl_stream_t stream);
 int b200ssl_peer_collect(b200ssl_peer_comm* comm, long long* ints_out, double* floats_out,
-                         b200ssl_stream_t post_stream, b200ssl_stream_t stream);
-int b200ssl_peer_join(b200ssl_peer_comm* comm, b200ssl_stream_t stream);
+                         b200ssl_stream_t stream);
 int b200ssl_peer_allreduce(b200ssl_peer_comm* comm, const long long* ints, int n_ints,
                            const float* const* floats_host, int n_floats, long long* ints_out,
                            double* floats_out, b200ssl_stream_t stream);
@@ -478,9 +482,9 @@ typedef struct b200ssl_step_desc {
   const b200ssl_ema_chunk* ema_table;
   int64_t ema_entries;
   double ema_alpha;
-  /* multi-GPU (optional): when `peer` is set the step ends by posting [cm || loss] to every rank and
-   * queues the collect on the communicator's own stream (lazy: b200ssl_peer_join before reading
-   * peer_cm_out [C*C] int64 / peer_loss_out [1] fp64 = sums over ranks) */
+  /* multi-GPU (optional): when `peer` is set the block that finalises the loss posts [cm || loss] to
+   * every rank and sums the PREVIOUS step's exchange into peer_cm_out [C*C] int64 / peer_loss_out [1]
+   * fp64 (no extra launch; b200ssl_peer_collect flushes the last step of a run) */
   struct b200ssl_peer_comm* peer;
   long long* peer_cm_out;
   double* peer_loss_out;

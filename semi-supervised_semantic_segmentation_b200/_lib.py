@@ -119,9 +119,8 @@ SIGNATURES = {
     "b200ssl_peer_mailbox": (_vp, [_vp]),
     "b200ssl_peer_connect": (_i, [_vp, _vp]),
     "b200ssl_peer_connect_ptrs": (_i, [_vp, _vp]),
-    "b200ssl_peer_post": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
-    "b200ssl_peer_collect": (_i, [_vp, _vp, _vp, _vp, _vp]),
-    "b200ssl_peer_join": (_i, [_vp, _vp]),
+    "b200ssl_peer_post": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "b200ssl_peer_collect": (_i, [_vp, _vp, _vp, _vp]),
     "b200ssl_peer_allreduce": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "b200ssl_peer_status": (_i, [_vp]),
     "b200ssl_peer_destroy": (_i, [_vp]),

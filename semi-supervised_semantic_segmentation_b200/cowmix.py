@@ -124,6 +124,29 @@ def upload_mask_parameters(p, sigmas, device):
     return size, st.upload(i, n * size + n)
 
 
+def stage_mask_parameters(p, sigmas, taps_dev):
+    """As upload_mask_parameters, but into a caller-owned device buffer [>= N*K + N floats] that keeps its
+    address from step to step (LossPathStep's static / CUDA-graph mode): the copy is ordered on the current
+    stream behind the previous step's readers of the buffer.  Returns the kernel size K."""
+    n = sigmas.shape[0]
+    size = kernel_size_for(sigmas.max().item())
+    nf = n * size + n
+    if taps_dev.numel() < nf:
+        raise ValueError(f"taps buffer holds {taps_dev.numel()} floats, K={size} needs {nf} "
+                         "(sigma outside the configured sigma_range?)")
+    device = taps_dev.device
+    st = _staging.get(device)
+    if st is None:
+        st = _staging[device] = _Staging(device)
+    i = st.slot(nf)
+    host = st.host[i]
+    gaussian_taps(size, sigmas.float(), out=host[: n * size].view(n, size))
+    torch.mul(p.mul(2).sub_(1).erfinv_(), _SQRT2, out=host[n * size: nf])
+    taps_dev[:nf].copy_(host[:nf], non_blocking=True)
+    st.events[i].record(torch.cuda.current_stream(device))
+    return size
+
+
 def masks_from_noise(noise, p, sigmas, return_field=False):
     """Deterministic tail of generate_cowmix_masks_like (cowmix.py:56-68) for a given noise field.
 

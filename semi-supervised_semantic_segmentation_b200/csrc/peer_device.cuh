@@ -1,5 +1,5 @@
 // Device side of the NVLink peer exchange (see peer.cu): shared with the kernels that post their own
-// results (the last Lovasz pass posts [confusion matrix || loss] from its finalising block).
+// results (the Lovasz finalising block posts [confusion matrix || loss] and collects the previous step).
 #pragma once
 #include "common.cuh"
 
@@ -10,13 +10,17 @@ constexpr int kPeerDepth = 4;
 constexpr int kPeerMaxWords = B200SSL_PEER_MAX_WORDS;
 constexpr int kPeerMaxFloats = B200SSL_PEER_MAX_FLOATS;
 constexpr size_t kAckOffset = (size_t)kPeerDepth * kPeerMaxRanks * kPeerMaxWords;  // in 8-byte words
-constexpr size_t kStatusOffset = kAckOffset + kPeerMaxRanks;
+constexpr size_t kStatusOffset = kAckOffset + kPeerMaxRanks;   // sticky time-out flag
+constexpr size_t kSeqOffset = kStatusOffset + 1;               // last step this rank posted     (local only)
+constexpr size_t kCollectedOffset = kStatusOffset + 2;         // last step this rank collected  (local only)
 constexpr size_t kMailWords = kStatusOffset + 16;
 
+// The sequence numbers live in DEVICE memory (the local mailbox), not in kernel arguments: a launch
+// carries no per-step state, so the whole step -- post and collect included -- can be captured once in a
+// CUDA graph and replayed, and a failed host call can never leave host and device counters out of step.
 struct PeerDev {  // by-value kernel parameter
   unsigned long long* mail[kPeerMaxRanks];
   int rank, world;
-  unsigned seq;
   unsigned long long timeout_ns;
 };
 
@@ -42,13 +46,18 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
-// Block-cooperative: every thread of the (single) block calls it.
-__device__ __forceinline__ void peer_post_block(const PeerDev& c, const long long* __restrict__ ints, int n_ints,
-                                const PeerFloats& f, int n_floats) {
+// Block-cooperative (every thread of the single block calls it): publishes the next step.  Returns its
+// sequence number to all threads.
+__device__ __forceinline__ unsigned peer_post_block(const PeerDev& c, const long long* __restrict__ ints, int n_ints,
+                                                    const PeerFloats& f, int n_floats) {
+  __shared__ unsigned s_seq;
   unsigned long long* me = c.mail[c.rank];
+  if (threadIdx.x == 0) s_seq = (unsigned)ld_sys(me + kSeqOffset) + 1u;
+  __syncthreads();
+  const unsigned seq = s_seq;
   // flow control: the slot of step seq was last used by step seq-depth
-  if ((int)threadIdx.x < c.world && c.seq > (unsigned)kPeerDepth) {
-    const unsigned need = c.seq - (unsigned)kPeerDepth;
+  if ((int)threadIdx.x < c.world && seq > (unsigned)kPeerDepth) {
+    const unsigned need = seq - (unsigned)kPeerDepth;
     const unsigned long long* a = me + kAckOffset + threadIdx.x;
     const unsigned long long t0 = global_ns();
     while ((int)((unsigned)ld_sys(a) - need) < 0) {
@@ -60,7 +69,7 @@ __device__ __forceinline__ void peer_post_block(const PeerDev& c, const long lon
     }
   }
   __syncthreads();
-  const int slot = (int)(c.seq % (unsigned)kPeerDepth);
+  const int slot = (int)(seq % (unsigned)kPeerDepth);
   const int nw = 2 * n_ints + n_floats;
   for (int w = threadIdx.x; w < nw; w += blockDim.x) {
     unsigned data;
@@ -70,24 +79,83 @@ __device__ __forceinline__ void peer_post_block(const PeerDev& c, const long lon
     } else {
       data = __float_as_uint(*f.p[w - 2 * n_ints]);
     }
-    const unsigned long long word = ((unsigned long long)c.seq << 32) | data;
+    const unsigned long long word = ((unsigned long long)seq << 32) | data;
     const size_t at = ll_index(slot, c.rank, w);
     for (int r = 0; r < c.world; ++r) st_sys(c.mail[(c.rank + r) % c.world] + at, word);
   }
+  if (threadIdx.x == 0) st_sys(me + kSeqOffset, (unsigned long long)seq);
+  return seq;
 }
 
+__device__ __forceinline__ unsigned peer_poll(const PeerDev& c, unsigned seq, const unsigned long long* p,
+                                              unsigned long long* status, bool* dead) {
+  unsigned long long v = ld_sys(p);
+  if ((unsigned)(v >> 32) == seq) return (unsigned)v;
+  if (*dead) return 0u;
+  const unsigned long long t0 = global_ns();
+  for (;;) {
+    v = ld_sys(p);
+    if ((unsigned)(v >> 32) == seq) return (unsigned)v;
+    if (global_ns() - t0 > c.timeout_ns) {
+      atomicExch(status, 2ull);
+      *dead = true;
+      return 0u;
+    }
+    __nanosleep(100);
+  }
+}
 
-// what a producing kernel needs to post on behalf of b200ssl_peer_post (filled by peer_begin_post)
+// Block-cooperative: sums the world rows of step `seq` in the LOCAL mailbox in rank order (int64 adds for
+// counts, fp64 adds for scalars: identical bits on every rank) unless that step has been collected
+// already, then acknowledges the slot to every peer.  seq == 0: nothing has been posted yet.
+__device__ __forceinline__ void peer_collect_block(const PeerDev& c, unsigned seq, int n_ints, int n_floats,
+                                                   long long* __restrict__ ints_out, double* __restrict__ floats_out) {
+  __shared__ unsigned s_done;
+  unsigned long long* me = c.mail[c.rank];
+  unsigned long long* status = me + kStatusOffset;
+  if (threadIdx.x == 0) s_done = (unsigned)ld_sys(me + kCollectedOffset);
+  __syncthreads();
+  if (seq == 0u || (int)(s_done - seq) >= 0) return;   // block-uniform
+  const int slot = (int)(seq % (unsigned)kPeerDepth);
+  bool dead = false;
+  for (int item = threadIdx.x; item < n_ints + n_floats; item += blockDim.x) {
+    if (item < n_ints) {
+      long long acc = 0;
+      for (int r = 0; r < c.world; ++r) {  // rank order: identical result on every rank
+        const unsigned lo = peer_poll(c, seq, me + ll_index(slot, r, 2 * item), status, &dead);
+        const unsigned hi = peer_poll(c, seq, me + ll_index(slot, r, 2 * item + 1), status, &dead);
+        acc += (long long)(((unsigned long long)hi << 32) | lo);
+      }
+      ints_out[item] = acc;
+    } else {
+      double acc = 0.0;
+      for (int r = 0; r < c.world; ++r)
+        acc += (double)__uint_as_float(peer_poll(c, seq, me + ll_index(slot, r, 2 * n_ints + (item - n_ints)), status, &dead));
+      floats_out[item - n_ints] = acc;
+    }
+  }
+  __syncthreads();
+  // every word of this slot has been consumed: tell the peers they may reuse it
+  if ((int)threadIdx.x < c.world) st_sys(c.mail[threadIdx.x] + kAckOffset + c.rank, (unsigned long long)seq);
+  if (threadIdx.x == 0) st_sys(me + kCollectedOffset, (unsigned long long)seq);
+}
+
+// What a producing kernel needs to run the exchange by itself (filled by peer_tail): it posts this step and,
+// when prev_* are given, collects the PREVIOUS step in the same block -- by then every peer has long posted
+// it, so the step costs no extra launch, event or stream for the collective and never waits unless a peer
+// is a whole step behind.
 struct PeerTail {
   PeerDev dev;
   const long long* ints;
   int n_ints;
   int enabled;
+  long long* prev_ints_out;
+  double* prev_floats_out;
 };
 
-int peer_begin_post(::b200ssl_peer_comm* c, int n_ints, int n_floats, PeerDev* out);          // peer.cu
+int peer_tail(::b200ssl_peer_comm* c, int n_ints, int n_floats, PeerTail* out);               // peer.cu
 int peer_post_impl(::b200ssl_peer_comm* c, const long long* ints, int n_ints, const float* const* floats_host,
-                   int n_floats, cudaStream_t s);                                             // peer.cu
+                   int n_floats, long long* prev_ints_out, double* prev_floats_out, cudaStream_t s);  // peer.cu
 int binary_lovasz_fused_impl(const float* scores, const float* target, int n_images, int n_channels, int64_t hw,
                              int cls, const float* grad_out, unsigned char* labels_out, int32_t* nonzero,
                              float* loss_out, float* denom_out, float* seg_loss, int32_t* seg_fg,

@@ -117,11 +117,12 @@ static int loss_path_step_on(const b200ssl_step_desc* d, b200ssl_stream_t s_mix,
       PeerTail tail = {};
       const bool fuse_post = d->peer && (!d->cm || !d->cm_labels) && fused_front_end_ok(d, hw);
       if (fuse_post) {
-        rc = peer_begin_post(d->peer, d->cm ? d->classes * d->classes : 0, 1, &tail.dev);
+        rc = peer_tail(d->peer, d->cm ? d->classes * d->classes : 0, 1, &tail);
         if (rc) return rc;
         tail.ints = d->cm;
         tail.n_ints = d->cm ? d->classes * d->classes : 0;
-        tail.enabled = 1;
+        tail.prev_ints_out = d->cm ? d->peer_cm_out : nullptr;
+        tail.prev_floats_out = d->peer_loss_out;
       }
       rc = binary_lovasz_fused_impl(d->scores, static_cast<const float*>(d->target), d->n, d->classes, hw, 1,
                                     grad_out, d->labels_u8, d->nonzero, loss, d->small + 1, d->seg_loss,
@@ -167,17 +168,16 @@ static int loss_path_step_on(const b200ssl_step_desc* d, b200ssl_stream_t s_mix,
       }
     }
   }
-  // 6. multi-GPU: post [cm || loss] into every rank's mailbox (unless the last Lovasz pass already did);
-  // the collect runs on the communicator's own stream, so this rank's streams never wait for a slower rank
+  // 6. multi-GPU: post [cm || loss] into every rank's mailbox and collect the PREVIOUS step into
+  // peer_cm_out / peer_loss_out (unless the Lovasz finalising block already did both)
   if (d->peer) {
     B200SSL_REQUIRE(d->scores && d->small, "loss_path_step: the peer exchange needs the Lovasz stage");
     if (!posted) {
       const float* scalars[1] = {d->small};
-      rc = peer_post_impl(d->peer, d->cm, d->cm ? d->classes * d->classes : 0, scalars, 1, (cudaStream_t)s_lovasz);
+      rc = peer_post_impl(d->peer, d->cm, d->cm ? d->classes * d->classes : 0, scalars, 1,
+                          d->cm ? d->peer_cm_out : nullptr, d->peer_loss_out, (cudaStream_t)s_lovasz);
       if (rc) return rc;
     }
-    rc = b200ssl_peer_collect(d->peer, d->peer_cm_out, d->peer_loss_out, s_lovasz, nullptr);
-    if (rc) return rc;
   }
   // 4. EMA over all parameters
   stream = s_ema;

@@ -146,9 +146,9 @@ class PeerAllReduce:
 
     torch.distributed is used ONCE, at construction, to exchange the 64-byte CUDA IPC handles of the
     mailboxes (and for the barriers around set-up and tear-down).  Per step every rank stores its
-    words directly into every rank's mailbox and a one-block kernel on the communicator's own
-    stream adds the rows in rank order; the caller's streams never wait for a slower rank until the
-    result is consumed (`result()` orders the current stream after the collect).
+    words directly into every rank's mailbox; the rows of step s-1 are added in rank order by the very
+    block that posts step s (no separate collect launch in steady state, sequence numbers on the device:
+    the step is CUDA-graph capturable); `result()` flushes the last step on the current stream.
 
     Results are sums over ranks: counts int64 (exact), scalars fp64 (fixed rank order, bit-identical
     on every rank).  Replaces the reference's `reduce_tensor` calls (utils/utils.py:43-54).
@@ -205,6 +205,7 @@ class PeerAllReduce:
                        torch.zeros(max(n_floats, 1), dtype=torch.float64, device=self.device))
                       for _ in range(_lib.PEER_DEPTH)]
         self._step = 0
+        self._pending = None          # (counts, scalars) of the last posted step
         self._closed = False
 
     @staticmethod
@@ -221,15 +222,23 @@ class PeerAllReduce:
     def handle(self):
         return self._comm
 
-    def next_outputs(self):
-        """(counts_out, scalars_out) tensors the NEXT exchange will fill (used by LossPathStep)."""
-        self._step += 1
-        return self._ring[self._step % len(self._ring)]
+    def begin_step(self, out=None):
+        """Bookkeeping for one posted step (used by LossPathStep and all_reduce): `out` = (counts int64,
+        scalars fp64) tensors that will receive this step's sums (default: the next pair of the internal
+        ring).  Returns (out, prev) where `prev` is the pair of the previous posted step -- the caller hands
+        it to the post as the fold-collect destination -- or None when there is no previous step."""
+        if out is None:
+            self._step += 1
+            out = self._ring[self._step % len(self._ring)]
+        prev, self._pending = self._pending, out
+        return out, prev
 
     def all_reduce(self, ints, floats, lazy=True):
         """ints: int64 tensor with n_ints elements (or None); floats: sequence of n_floats fp32 0-dim
-        tensors.  Issues post + collect; returns (counts, scalars) tensors that are valid on the
-        current stream after `result()` (lazy=True) or immediately in stream order (lazy=False)."""
+        tensors.  lazy=True: posts this step and, in the same launch, completes the previous step's
+        exchange; the returned (counts, scalars) tensors are valid on the current stream after `result()`
+        (or after the next lazy all_reduce).  lazy=False: post + collect of this step in one launch; the
+        current stream then waits for the slowest rank's post."""
         C, lib = self._C, self._lib.lib
         if len(floats) != self.n_floats:
             raise ValueError(f"PeerAllReduce: expected {self.n_floats} scalars, got {len(floats)}")
@@ -239,21 +248,33 @@ class PeerAllReduce:
                 raise ValueError("PeerAllReduce: counts must be a contiguous int64 tensor of n_ints elements")
         fl = [self._lib.require_cuda(f, "scalar", torch.float32) for f in floats]
         fptrs = (C.c_void_p * max(len(fl), 1))(*[f.data_ptr() for f in fl])
-        out_i, out_f = self.next_outputs()
+        (out_i, out_f), prev = self.begin_step()
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        iptr = ints.data_ptr() if self.n_ints else None
         with torch.cuda.device(self.device):
-            self._lib.check(lib.b200ssl_peer_post(self._comm, ints.data_ptr() if self.n_ints else None, self.n_ints,
-                                                  fptrs, self.n_floats, stream), "peer_post")
-            self._lib.check(lib.b200ssl_peer_collect(self._comm, out_i.data_ptr(), out_f.data_ptr(), stream,
-                                                     None if lazy else stream), "peer_collect")
+            if lazy:
+                self._lib.check(lib.b200ssl_peer_post(self._comm, iptr, self.n_ints, fptrs, self.n_floats,
+                                                      prev[0].data_ptr() if prev else None,
+                                                      prev[1].data_ptr() if prev else None, stream), "peer_post")
+            else:
+                if prev is not None:      # an earlier lazy step must not stay uncollected behind this one
+                    self._lib.check(lib.b200ssl_peer_collect(self._comm, prev[0].data_ptr(), prev[1].data_ptr(),
+                                                             stream), "peer_collect")
+                self._lib.check(lib.b200ssl_peer_allreduce(self._comm, iptr, self.n_ints, fptrs, self.n_floats,
+                                                           out_i.data_ptr(), out_f.data_ptr(), stream),
+                                "peer_allreduce")
         return out_i[:self.n_ints], out_f[:self.n_floats]
 
     def result(self):
-        """Order the current stream after the last collect and return its (counts, scalars)."""
+        """Complete the exchange of the last posted step on the current stream (a no-op on the device if
+        it has already been collected) and return its (counts, scalars)."""
+        if self._pending is None:
+            raise RuntimeError("PeerAllReduce.result: nothing has been posted")
+        out_i, out_f = self._pending
         stream = self._C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         with torch.cuda.device(self.device):
-            self._lib.check(self._lib.lib.b200ssl_peer_join(self._comm, stream), "peer_join")
-        out_i, out_f = self._ring[self._step % len(self._ring)]
+            self._lib.check(self._lib.lib.b200ssl_peer_collect(self._comm, out_i.data_ptr(), out_f.data_ptr(),
+                                                               stream), "peer_collect")
         return out_i[:self.n_ints], out_f[:self.n_floats]
 
     def status(self):

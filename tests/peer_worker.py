@@ -49,18 +49,40 @@ def main():
     blob = torch.nn.functional.avg_pool2d(torch.randn(n, cc, h, w, generator=g), 9, 1, 4)
     target = torch.nn.functional.one_hot(blob.argmax(1), cc).permute(0, 3, 1, 2).float().contiguous().to(dev)
     params, ema = [torch.randn(100, generator=g).to(dev)], [torch.randn(100, generator=g).to(dev)]
-    for _ in range(9):
-        out = step(img[0], img[1], tea[0], tea[1], scores, target, params, ema)
-        peer.result()
-        want_cm = out["cm"].clone()
-        want_loss = out["loss"].double().reshape(1).clone()
-        dist.all_reduce(want_cm)
-        dist.all_reduce(want_loss)
+    def run(step_obj, peer_obj, rounds, flush_every):
+        last = None
+        for it in range(rounds):
+            out = step_obj(img[0], img[1], tea[0], tea[1], scores, target, params, ema)
+            want_cm = out["cm"].clone()
+            want_loss = out["loss"].double().reshape(1).clone()
+            dist.all_reduce(want_cm)
+            dist.all_reduce(want_loss)
+            flushed = (it % flush_every) == flush_every - 1
+            if flushed:
+                peer_obj.result()
+            torch.cuda.synchronize(dev)
+            checks = [(out, want_cm, want_loss)] if flushed else []
+            if last is not None:
+                checks.append(last)                       # completed by THIS step's post (fold-collect)
+            for o, wc, wl in checks:
+                assert torch.equal(o["cm_sum"], wc), rank
+                assert torch.allclose(o["loss_sum"].reshape(1), wl, rtol=1e-15, atol=0), rank
+            last = (dict(cm_sum=out["cm_sum"].clone() if flushed else out["cm_sum"], loss_sum=out["loss_sum"]),
+                    want_cm, want_loss)
+        peer_obj.result()
         torch.cuda.synchronize(dev)
-        assert torch.equal(out["cm_sum"], want_cm), rank
-        assert torch.allclose(out["loss_sum"].reshape(1), want_loss, rtol=1e-15, atol=0), rank
+        assert torch.equal(last[0]["cm_sum"], last[1]), rank
+
+    run(step, peer, 9, 3)
     peer.status()
     peer.close()
+    # the same through CUDA graphs: replayed posts/collects take their sequence numbers from device memory
+    peer_g = b200ssl.utils.PeerAllReduce(cc * cc, 1, dev)
+    step_g = b200ssl.LossPathStep(num_classes=cc, sigma_range=(2, 4), peer=peer_g, graph=True, ring=2)
+    run(step_g, peer_g, 12, 4)
+    assert step_g.graph_captures < 12 * 2
+    peer_g.status()
+    peer_g.close()
     red.peer.close()
     dist.barrier()
     if rank == 0:

@@ -39,6 +39,7 @@ def test_inprocess_ranks_sum_exactly(utils, world, n_ints, n_floats, lazy):
     streams = [torch.cuda.Stream(dev) for _ in range(world)]
     gen = torch.Generator().manual_seed(world * 1000 + n_ints)
     steps = 11                                            # > 2 trips around the 4-deep slot ring
+    pending = None
     for step in range(steps):
         ints = torch.randint(-2**40, 2**40, (world, max(n_ints, 1)), generator=gen, dtype=torch.int64)
         floats = torch.randn(world, max(n_floats, 1), generator=gen) * 10.0
@@ -46,13 +47,19 @@ def test_inprocess_ranks_sum_exactly(utils, world, n_ints, n_floats, lazy):
         torch.cuda.synchronize(dev)
         outs = [None] * world
         if lazy:
+            # lazy: the post of step s also completes step s-1 (checked below through `pending`); result()
+            # flushes step s on the rank's stream
             for r in range(world):
                 with torch.cuda.stream(streams[r]):
                     comms[r].all_reduce(d_ints[r, :n_ints] if n_ints else None,
                                         [d_floats[r, i] for i in range(n_floats)], lazy=True)
-            for r in range(world):
-                with torch.cuda.stream(streams[r]):
-                    outs[r] = tuple(t.clone() for t in comms[r].result())
+            if step % 3 != 2:                             # every third step is left to the NEXT post's fold-collect
+                for r in range(world):
+                    with torch.cuda.stream(streams[r]):
+                        outs[r] = tuple(t.clone() for t in comms[r].result())
+            else:
+                pending = (ints, floats, [c._pending for c in comms])
+                continue
         else:
             # non-lazy collects spin on their own stream until every rank has posted: issue all the
             # posts first (one rank's blocking collect must never sit in front of another's post)
@@ -63,31 +70,44 @@ def test_inprocess_ranks_sum_exactly(utils, world, n_ints, n_floats, lazy):
                 fl = [d_floats[r, i] for i in range(n_floats)]
                 fptrs = (C.c_void_p * max(n_floats, 1))(*[f.data_ptr() for f in fl])
                 _lib.check(_lib.lib.b200ssl_peer_post(comms[r].handle, d_ints[r].data_ptr() if n_ints else None, n_ints,
-                                                      fptrs, n_floats, C.c_void_p(streams[r].cuda_stream)))
+                                                      fptrs, n_floats, None, None, C.c_void_p(streams[r].cuda_stream)))
             for r in range(world):
                 oi = torch.zeros(max(n_ints, 1), dtype=torch.int64, device=dev)
                 of = torch.zeros(max(n_floats, 1), dtype=torch.float64, device=dev)
                 s = C.c_void_p(streams[r].cuda_stream)
-                _lib.check(_lib.lib.b200ssl_peer_collect(comms[r].handle, oi.data_ptr(), of.data_ptr(), s, s))
+                _lib.check(_lib.lib.b200ssl_peer_collect(comms[r].handle, oi.data_ptr(), of.data_ptr(), s))
+                _lib.check(_lib.lib.b200ssl_peer_collect(comms[r].handle, oi.data_ptr(), of.data_ptr(), s))  # idempotent
                 res.append((oi[:n_ints], of[:n_floats]))
             outs = res
         torch.cuda.synchronize(dev)
-        want_i = ints[:, :n_ints].sum(0)
-        want_f = torch.zeros(n_floats, dtype=torch.float64)
-        for r in range(world):                            # rank order, fp64, like the kernel
-            want_f = want_f + floats[r, :n_floats].double()
+
+        def expect(ints, floats):
+            want_i = ints[:, :n_ints].sum(0)
+            want_f = torch.zeros(n_floats, dtype=torch.float64)
+            for r in range(world):                        # rank order, fp64, like the kernel
+                want_f = want_f + floats[r, :n_floats].double()
+            return want_i, want_f
+
+        def same(got, want):
+            return torch.equal(got[0].cpu(), want[0]) and \
+                np.array_equal(got[1].cpu().numpy().view(np.uint64), want[1].numpy().view(np.uint64))
+
         for r in range(world):
-            gi, gf = outs[r]
-            assert torch.equal(gi.cpu(), want_i), (step, r)
-            assert np.array_equal(gf.cpu().numpy().view(np.uint64), want_f.numpy().view(np.uint64)), (step, r)
+            assert same(outs[r], expect(ints, floats)), (step, r)
+        if pending is not None:                           # the step that was only completed by this step's post
+            p_ints, p_floats, bufs = pending
+            for r in range(world):
+                assert same((bufs[r][0][:n_ints], bufs[r][1][:n_floats]), expect(p_ints, p_floats)), (step, r, "folded")
+            pending = None
     for c in comms:
         c.status()
     for c in comms:
         c.close(barrier=False)
 
 
-def test_post_runs_ahead_without_blocking_until_ring_is_full(utils):
-    """Rank 0 may post depth-1 steps before rank 1 has collected anything; everything still sums."""
+def test_rank_issued_ahead_of_its_peer_still_sums(utils):
+    """Rank 0's three steps are issued before rank 1 has issued anything: its fold-collects of steps 1 and 2
+    wait (on rank 0's stream only) until rank 1's posts arrive, nothing deadlocks, everything sums."""
     dev = torch.device("cuda:0")
     comms = _make(utils, 2, 1, 1, dev)
     s0, s1 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -143,12 +163,19 @@ def test_loss_path_step_with_peer_world1(utils):
     target = torch.nn.functional.one_hot(blob.argmax(1), c).permute(0, 3, 1, 2).float().contiguous().to(dev)
     params = [torch.randn(100, generator=g).to(dev)]
     ema = [torch.randn(100, generator=g).to(dev)]
-    for _ in range(6):
+    last = None
+    for it in range(6):
         out = step(img[0], img[1], tea[0], tea[1], scores, target, params, ema)
-        peer.result()
+        if it % 2:
+            peer.result()                                 # explicit flush of this step ...
         torch.cuda.synchronize(dev)
-        assert torch.equal(out["cm_sum"], out["cm"])
-        assert float(out["loss_sum"]) == float(out["loss"].double())
+        if last is not None:                              # ... or completed by the next step's post
+            assert torch.equal(last["cm_sum"], last["cm"])
+            assert float(last["loss_sum"]) == float(last["loss"].double())
+        if it % 2:
+            assert torch.equal(out["cm_sum"], out["cm"])
+            assert float(out["loss_sum"]) == float(out["loss"].double())
+        last = out
     peer.status()
     peer.close()
 
