@@ -201,14 +201,22 @@ def sync_all(device, world):
         torch.cuda.synchronize(device)
 
 
-def timed_regions(one_step, steps, n_regions, device, world, end_region=None, clocks=None, debug=None):
+def timed_regions(one_step, steps, n_regions, device, world, end_region=None, clocks=None, debug=None,
+                  per_rank_log=None):
     """n_regions back-to-back regions of EXACTLY `steps` steps, each bracketed by barrier + synchronize on both
     sides and timed with CUDA events on the issuing stream; per region the MAX over ranks.  `end_region`
     (multi-GPU: the flush of the last step's exchange) is issued inside the region, before the stop event."""
     out = []
+    align = torch.zeros(1, device=device) if world > 1 else None
     for rep in range(n_regions):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync_all(device, world)
+        if world > 1:
+            # The host-side barrier releases the ranks tens of microseconds apart; the steps exchange data every
+            # step, so the early rank would absorb that skew INSIDE its timed region (it waits for the late rank's
+            # first post).  A device-side rendezvous queued right before the start event aligns the GPU timelines
+            # to a few microseconds instead; it is outside the region on every rank.
+            dist.all_reduce(align)
         if clocks is not None:
             clocks.active = True
         e0.record()
@@ -229,6 +237,10 @@ def timed_regions(one_step, steps, n_regions, device, world, end_region=None, cl
                   f"host sum {sum(t_host) * 1e3:.1f} ms, device {e0.elapsed_time(e1):.1f} ms", file=sys.stderr)
         t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
         if world > 1:
+            per_rank = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(per_rank, t)
+            if per_rank_log is not None:
+                per_rank_log.append([round(float(x), 4) for x in per_rank])
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out.append(float(t))
     return out
@@ -361,8 +373,9 @@ def measure_step_config(b200ssl, cfg, args, rank, world, device, headline, clock
     steps = args.steps if headline else max(3, min(args.steps, 20))
     n_regions = max(3, math.ceil(MIN_TIMED_STEPS / steps)) if headline else 3
     l0 = _lib.launch_count()
+    per_rank_log = []
     region_ms = timed_regions(one_step, steps, n_regions, device, world, end_region, clocks if headline else None,
-                              debug=(cfg["key"] if debug else None))
+                              debug=(cfg["key"] if debug else None), per_rank_log=per_rank_log)
     launches = (_lib.launch_count() - l0) // n_regions
     ms_step_all = sum(region_ms) / (n_regions * steps)            # every timed step counts (no region is dropped)
     value = world * P / (ms_step_all * 1e-3) / 1e6
@@ -407,6 +420,7 @@ def measure_step_config(b200ssl, cfg, args, rank, world, device, headline, clock
         res["collective"] = ("[cm || loss] over NVLink peer memory (b200ssl_peer_*): step s posted and step s-1 collected by "
                              "the Lovasz finalising block, last step flushed inside the timed region" if peer is not None
                              else "one torch.distributed (NCCL) all_reduce of [cm || loss] per step")
+        res["region_ms_per_rank"] = per_rank_log[:4]
         res["ema_share_of_step_bytes"] = round(12 * n_params / step_algorithmic_bytes(P, cfg["c"], n_params), 4)
 
     # ---- per-kernel / per-stage table (explains the number above) ----
@@ -778,7 +792,8 @@ def run_b200(args, rank, world, local_rank):
         "clocks": clock_info, "e2e": e2e, "gpu_launches": head["gpu_launches_per_region"],
         "roofline": head["roofline"],
     }
-    for k in ("collective", "collective_check", "ema_share_of_step_bytes", "aten_cuda_baseline", "cpu_baseline"):
+    for k in ("collective", "collective_check", "region_ms_per_rank", "ema_share_of_step_bytes", "aten_cuda_baseline",
+              "cpu_baseline"):
         if k in head:
             line[k] = head[k]
     if extra:
