@@ -271,6 +271,15 @@ int b200ssl_dice_metric(const float* input, const float* target, int n, int64_t 
                         b200ssl_stream_t stream);
 size_t b200ssl_dice_workspace_bytes(int n, int64_t chw);
 
+/* The validation metric of train.py:171-175 in one pass: argmax over the channels of logits [n,C,h,w] (the
+ * network's resolution), one_hot, `nearest` resize to the mask size (src = min(floor(dst * in/out), in-1), in/out
+ * in fp32 like ATen), mask[:, fg] > threshold.  Accumulates the per-image 2x2 matrices cm_per_image [n][4] =
+ * {TN, FP, FN, TP} (int64, caller zeroes them; streaming evaluation may accumulate); b200ssl_dice_from_cm then
+ * gives metrics.dice_metric (metrics.py:1-7) of (pred_map_binary[:, 1:], mask_binary[:, 1:]) exactly. */
+int b200ssl_validation_cm(const float* logits, int n, int n_channels, int h, int w, const float* mask,
+                          int mask_channels, int H, int W, float threshold, int fg_class, long long* cm_per_image,
+                          b200ssl_stream_t stream);
+
 /* the same quantity from per-image 2x2 confusion matrices [n][4] = {TN, FP, FN, TP}:
  *   dice[n] = (2*TP + 1) / (2*TP + FP + FN + 1)  evaluated in fp32 like the reference. */
 int b200ssl_dice_from_cm(const long long* cm_per_image, int n_images, float* dice_out,
@@ -372,6 +381,24 @@ int b200ssl_grad_scale_multi(const b200ssl_sgd_chunk* table_dev, int64_t n_entri
                              b200ssl_stream_t stream);
 int b200ssl_sgd_ema_multi(const b200ssl_sgd_chunk* table_dev, int64_t n_entries, const float* coef_dev,
                           const b200ssl_sgd_hyper* hyper, b200ssl_stream_t stream);
+
+/* Row N2, student side: losses.CalculateLoss (losses.py:15-22: F.interpolate of every prediction to
+ * the target size, bilinear, align_corners=False) + binary_lovasz_loss_with_logits (losses.py:239-250) computed
+ * straight from LOW-RESOLUTION logits scores_low [n,C,low_h,low_w]: the fused front end interpolates channel
+ * `cls` in registers (ATen's upsample_bilinear2d arithmetic) while it builds the sort words, the last radix pass
+ * scatters dLoss/d(up-sampled logit) into the one-channel scratch plane grad_full [n,H,W], and the transposed
+ * interpolation gathers it -- deterministically, no floating-point atomics -- into grad_low [n,C,low_h,low_w]
+ * (zero for channels other than `cls`).  Workspace: b200ssl_lovasz_workspace_bytes of the descriptor
+ * {n, 1 channel, H*W, per_image, class list [cls], ignore 255, uint8 labels}.  Returns B200SSL_EUNSUPPORTED
+ * (nothing launched) unless W % 4 == 0, target is 16-byte aligned and the up-sampling ratio is <= 9.
+ * b200ssl_upsample_bilinear_backward is the stand-alone transposed interpolation of dense planes. */
+int b200ssl_binary_lovasz_lowres(const float* scores_low, const float* target, int n_images, int n_channels,
+                                 int low_h, int low_w, int H, int W, int cls, const float* grad_out,
+                                 unsigned char* labels_out, int32_t* nonzero, float* loss_out, float* denom_out,
+                                 float* seg_loss, int32_t* seg_fg, int32_t* seg_valid, float* grad_full,
+                                 float* grad_low, void* workspace, size_t workspace_bytes, b200ssl_stream_t stream);
+int b200ssl_upsample_bilinear_backward(const float* grad_full, int64_t planes, int H, int W, float* grad_low,
+                                       int low_h, int low_w, b200ssl_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Per-step all-reduce over NVLink peer memory.  Replaces utils/utils.py:43-54

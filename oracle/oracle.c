@@ -246,6 +246,61 @@ ORC_API void orc_upsample_bilinear(const float* in, long long planes, int h, int
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Row N2, student side: the backward of F.interpolate(.., 'bilinear', align_corners=False) (autograd's
+ * upsample_bilinear2d_backward behind losses.py:18-19) as the deterministic gather the CUDA kernel
+ * computes: for a low-resolution pixel (iy, ix) the output pixels whose taps touch it are visited in
+ * ascending (y, x) order, acc = fma(RN(wy * wx), g, acc), wy = [i0(y) == iy] * (1 - ly) + [i1(y) == iy] * ly.
+ * ATen adds the same products (CPU: in output order per tap; CUDA: atomically), so this agrees with
+ * autograd to rounding (<= 1e-5 relative in L2, tests/golden/lowres_lovasz.npz), not bit for bit.
+ * ------------------------------------------------------------------------------------------ */
+static void orc_axis_tap(int dst, int in, float scale, int* i0, int* i1, float* w0, float* w1) {
+  float s = fmaf(scale, (float)dst + 0.5f, -0.5f);
+  if (s < 0.f) s = 0.f;
+  int a = (int)floorf(s);
+  if (a > in - 1) a = in - 1;
+  float l = s - (float)a;
+  l = l < 0.f ? 0.f : (l > 1.f ? 1.f : l);
+  *i0 = a;
+  *i1 = a + (a < in - 1 ? 1 : 0);
+  *w0 = 1.0f - l;
+  *w1 = l;
+}
+
+ORC_API void orc_upsample_bilinear_backward(const float* gfull, long long planes, int H, int W, float* glow, int h,
+                                            int w) {
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  for (long long p = 0; p < planes; ++p) {
+    const float* g = gfull + (size_t)p * H * W;
+    float* o = glow + (size_t)p * h * w;
+    for (int iy = 0; iy < h; ++iy)
+      for (int ix = 0; ix < w; ++ix) {
+        /* generous integer windows: every pixel outside the true support has weight 0 and is skipped */
+        long long y_lo = (long long)(iy - 1) * H / h - 2, y_hi = (long long)(iy + 2) * H / h + 2;
+        long long x_lo = (long long)(ix - 1) * W / w - 2, x_hi = (long long)(ix + 2) * W / w + 2;
+        if (y_lo < 0) y_lo = 0;
+        if (x_lo < 0) x_lo = 0;
+        if (y_hi > H - 1) y_hi = H - 1;
+        if (x_hi > W - 1) x_hi = W - 1;
+        float acc = 0.f;
+        for (long long y = y_lo; y <= y_hi; ++y) {
+          int i0, i1;
+          float w0, w1;
+          orc_axis_tap((int)y, h, sy, &i0, &i1, &w0, &w1);
+          const float wy = (i0 == iy ? w0 : 0.f) + (i1 == iy ? w1 : 0.f);
+          if (wy == 0.f) continue;
+          for (long long x = x_lo; x <= x_hi; ++x) {
+            orc_axis_tap((int)x, w, sx, &i0, &i1, &w0, &w1);
+            const float wx = (i0 == ix ? w0 : 0.f) + (i1 == ix ? w1 : 0.f);
+            if (wx == 0.f) continue;
+            acc = fmaf(wy * wx, g[(size_t)y * W + x], acc);
+          }
+        }
+        o[(size_t)iy * w + ix] = acc;
+      }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
  * Row N4: train.py:122-124,130 -- clip_grad_norm_ -> torch.optim.SGD.step -> EMA, per element:
  *   g = RN(g*coef) (only when clipping); g = fmaf(p, wd, g) (wd != 0);
  *   b = first ? g : fmaf(g, 1-damp, RN(b*mu)); d = nesterov ? fmaf(b, mu, g) : b  (mu != 0);

@@ -99,6 +99,7 @@ SIGNATURES = {
     "b200ssl_dice_workspace_bytes": (_sz, [_i, _i64]),
     "b200ssl_dice_metric": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _sz, _vp]),
     "b200ssl_dice_from_cm": (_i, [_vp, _i, _vp, _vp]),
+    "b200ssl_validation_cm": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, C.c_float, _i, _vp, _vp]),
     "b200ssl_consistency_workspace_bytes": (_sz, [_i, _i64]),
     "b200ssl_consistency_forward": (_i, [_vp, _vp, _i, _i, _i64, C.c_float, _vp, _vp, _sz, _vp]),
     "b200ssl_consistency_backward": (_i, [_vp, _vp, _i, _i, _i64, C.c_float, _vp, _vp, _vp, _vp]),
@@ -110,6 +111,8 @@ SIGNATURES = {
     "b200ssl_softmax_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i64, _vp]),
     "b200ssl_mix2_upsampled": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     "b200ssl_upsample_bilinear": (_i, [_vp, _i64, _i, _i, _vp, _i, _i, _vp]),
+    "b200ssl_upsample_bilinear_backward": (_i, [_vp, _i64, _i, _i, _vp, _i, _i, _vp]),
+    "b200ssl_binary_lovasz_lowres": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i] + [_vp] * 10 + [_vp, _sz, _vp]),
     "b200ssl_sgd_build_table_host": (_i64, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i64]),
     "b200ssl_grad_norm_workspace_bytes": (_sz, [_i64]),
     "b200ssl_grad_norm_multi": (_i, [_vp, _i64, _d, _vp, _vp, _sz, _vp]),

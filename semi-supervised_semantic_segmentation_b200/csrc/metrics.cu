@@ -121,6 +121,53 @@ static int dice_blocks(int n, long long chw) {
   return (int)bx;
 }
 
+// ------------------------------------------------------------------------------------------
+// Validation metric in one pass (train.py:171-175): argmax over the channels of the LOW-RESOLUTION logits,
+// one_hot, nearest-neighbour resize to the mask size, mask > 0.5, Dice of channel `fg` -- six ATen kernels and
+// three full-resolution temporaries in the reference.  Here every mask pixel looks up the argmax of its
+// nearest low-resolution source pixel (ATen `nearest`: src = min(floor(dst * in/out), in - 1) with in/out
+// evaluated in fp32) and the per-image 2x2 confusion matrix {TN, FP, FN, TP} of (mask > thr, argmax == fg)
+// is accumulated as integers; b200ssl_dice_from_cm turns it into metrics.py:1-7's value.
+// grid = (blocks, n); mask channel `fg` of mask [n, mask_channels, H, W].
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+validation_cm_kernel(const float* __restrict__ logits, int C, int h, int w, const float* __restrict__ mask,
+                     int mask_channels, int H, int W, float thr, int fg, unsigned long long* __restrict__ cm) {
+  const int n = blockIdx.y;
+  const float* __restrict__ lp = logits + (long long)n * C * h * w;
+  const float* __restrict__ mp = mask + ((long long)n * mask_channels + fg) * (long long)H * W;
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  unsigned cnt[4] = {0u, 0u, 0u, 0u};
+  const long long hw_low = (long long)h * w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)H * W;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / W), x = (int)(i - (long long)y * W);
+    const int ys = min((int)floorf((float)y * sy), h - 1), xs = min((int)floorf((float)x * sx), w - 1);
+    const float* __restrict__ q = lp + (long long)ys * w + xs;
+    float best = __ldg(q);
+    int arg = 0;
+    for (int c = 1; c < C; ++c) {   // torch.argmax: first maximum wins, NaN counts as the maximum
+      const float v = __ldg(q + c * hw_low);
+      if (v > best || (v != v && best == best)) { best = v; arg = c; }
+    }
+    const int p_fg = arg == fg ? 1 : 0;
+    const int m_fg = ld_stream_f1(mp + i) > thr ? 1 : 0;
+    cnt[m_fg * 2 + p_fg] += 1u;
+  }
+  __shared__ unsigned red[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const unsigned t = warp_sum(cnt[k]);
+    if (lane_id() == 0) red[k][threadIdx.x >> 5] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    unsigned long long t = 0;
+    for (int wv = 0; wv < 8; ++wv) t += red[threadIdx.x][wv];
+    if (t) atomicAdd(cm + (long long)n * 4 + threadIdx.x, t);
+  }
+}
+
 }  // namespace b200ssl
 
 extern "C" {
@@ -179,6 +226,27 @@ int b200ssl_dice_metric(const float* input, const float* target, int n, int64_t 
   prof_begin("dice_final", s);
   dice_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(static_cast<const double*>(workspace), bx, n, dice_out);
   return check_launch("dice final");
+}
+
+int b200ssl_validation_cm(const float* logits, int n, int n_channels, int h, int w, const float* mask,
+                          int mask_channels, int H, int W, float threshold, int fg_class, long long* cm_per_image,
+                          b200ssl_stream_t stream) {
+  using namespace b200ssl;
+  B200SSL_REQUIRE(n >= 0 && n_channels >= 1 && h >= 1 && w >= 1 && H >= 0 && W >= 0 && mask_channels >= 1,
+                  "validation_cm: bad extents");
+  B200SSL_REQUIRE(fg_class >= 0 && fg_class < mask_channels, "validation_cm: class %d not in the mask", fg_class);
+  B200SSL_REQUIRE(n <= 65535, "validation_cm: too many samples");
+  if (n == 0 || H == 0 || W == 0) return 0;
+  B200SSL_REQUIRE(logits && mask && cm_per_image, "validation_cm: null argument");
+  long long bx = ((long long)H * W + 256 * 8 - 1) / (256 * 8);
+  long long cap = (long long)kNumSMs * 8 / n;
+  if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  prof_begin("validation_cm", (cudaStream_t)stream);
+  validation_cm_kernel<<<dim3((unsigned)bx, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(
+      logits, n_channels, h, w, mask, mask_channels, H, W, threshold, fg_class,
+      reinterpret_cast<unsigned long long*>(cm_per_image));
+  return check_launch("validation_cm");
 }
 
 }  // extern "C"

@@ -20,12 +20,23 @@ class CalculateLoss():
         self.losses = losses
 
     def __call__(self, predictions_list, target):
+        """losses.py:15-22.  Row N2: a loss_fn that declares `accepts_lowres` (this module's
+        binary_lovasz_loss_with_logits) is handed the prediction at ITS resolution and interpolates inside its
+        own kernels; the full-resolution prediction is only materialised when some other loss_fn needs it."""
         loss = 0
         for prediction_idx, prediction in enumerate(predictions_list):
-            prediction = torch.nn.functional.interpolate(prediction, size=(target.size(2), target.size(3)),
-                                                         mode='bilinear', align_corners=False)
+            size = (target.size(2), target.size(3))
+            full = None
             for loss_spec in self.losses:
-                loss += loss_spec['loss_fn'](prediction, target) * loss_spec['weight'][prediction_idx]
+                fn = loss_spec['loss_fn']
+                if getattr(fn, "accepts_lowres", False) and prediction.is_cuda and _lowres_ok(prediction, target):
+                    value = fn(prediction, target)
+                else:
+                    if full is None:
+                        full = torch.nn.functional.interpolate(prediction, size=size, mode='bilinear',
+                                                               align_corners=False)
+                    value = fn(full, target)
+                loss += value * loss_spec['weight'][prediction_idx]
         return loss
 
 
@@ -80,13 +91,75 @@ class _BinaryReduce(torch.autograd.Function):
         return scale, None
 
 
+_MAX_UPSAMPLE_RATIO = 9.0   # csrc/lovasz.cu: kMaxBackWin
+
+
+def _lowres_ok(prediction, target):
+    """shapes the fused low-resolution front end takes (else the caller interpolates with torch)"""
+    return (prediction.dim() == 4 and target.dim() == 4 and prediction.dtype == torch.float32 and
+            prediction.shape[:2] == target.shape[:2] and prediction.shape[1] >= 2 and target.shape[3] % 4 == 0 and
+            1 <= prediction.shape[2] <= target.shape[2] and 1 <= prediction.shape[3] <= target.shape[3] and
+            target.shape[3] / prediction.shape[3] <= _MAX_UPSAMPLE_RATIO and
+            (target.shape[2] != prediction.shape[2] or target.shape[3] != prediction.shape[3]))
+
+
+class _BinaryLovaszLowres(torch.autograd.Function):
+    """CalculateLoss's bilinear resize (losses.py:18-19) + binary_lovasz_loss_with_logits (:239-250) from
+    low-resolution logits in one chain of kernels (b200ssl_binary_lovasz_lowres).  The loss is linear in its
+    upstream gradient, so forward computes d loss / d input for an upstream 1 and backward scales it."""
+
+    @staticmethod
+    def forward(ctx, input_low, target):
+        dev = input_low.device
+        n, c, lh, lw = input_low.shape
+        H, W = target.shape[2], target.shape[3]
+        desc = _lib.LovaszDesc()
+        desc.n_images, desc.n_channels, desc.hw = n, 1, H * W
+        desc.per_image, desc.class_mode, desc.n_list = 1, _lib.LOVASZ_LIST, 1
+        desc.class_list[0] = 1
+        desc.has_ignore, desc.ignore_index, desc.label_dtype = 1, 255, _lib.U8
+        ws = _lib.workspaces.get(dev, "lovasz", lib.b200ssl_lovasz_workspace_bytes(C.byref(desc)))
+        small = torch.empty(3, dtype=torch.float32, device=dev)                 # loss, denom, upstream 1.0
+        small[2] = 1.0
+        segf = torch.empty(n, dtype=torch.float32, device=dev)
+        segi = torch.empty(3 * n, dtype=torch.int32, device=dev)                # seg_fg | seg_valid | nonzero
+        labels = torch.empty((n, H, W), dtype=torch.uint8, device=dev)
+        grad_full = torch.empty((n, H, W), dtype=torch.float32, device=dev)     # d loss / d up-sampled logit of class 1
+        grad_low = torch.empty_like(input_low)
+        with torch.cuda.device(dev):
+            check(lib.b200ssl_binary_lovasz_lowres(
+                input_low.data_ptr(), target.data_ptr(), n, c, lh, lw, H, W, 1, small.data_ptr() + 8,
+                labels.data_ptr(), segi.data_ptr() + 8 * n, small.data_ptr(), small.data_ptr() + 4, segf.data_ptr(),
+                segi.data_ptr(), segi.data_ptr() + 4 * n, grad_full.data_ptr(), grad_low.data_ptr(), ws.data_ptr(),
+                ws.numel(), stream_ptr(dev)), "binary_lovasz_lowres")
+        ctx.save_for_backward(grad_low)
+        return small[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad_low,) = ctx.saved_tensors
+        return grad_low * g.to(torch.float32), None
+
+
 def binary_lovasz_loss_with_logits(input, target):
     """losses.py:239-250.  `input` are raw logits (the reference's sigmoid is commented out),
     `target` a soft one-hot [N,C,H,W]; class 1 only, void label 255, one Lovasz problem per image,
-    images without any non-zero label get weight 0."""
+    images without any non-zero label get weight 0.
+    Row N2: `input` may be at a LOWER resolution than `target` (the network's stride-4 logits); it is then
+    bilinearly up-sampled (align_corners=False, as losses.py:18-19 does before calling the loss) inside the
+    front end of the sort and the gradient comes back at the input's resolution."""
     require_cuda(input, "input", torch.float32)
     if input.shape[0] == 0:
         raise ValueError("binary_lovasz_loss_with_logits needs a non-empty batch")
+    if input.dim() == 4 and target.dim() == 4 and input.shape[2:] != target.shape[2:]:
+        require_cuda(target, "target", torch.float32)
+        if _lowres_ok(input, target):
+            return _BinaryLovaszLowres.apply(input.contiguous(), target.contiguous())
+        input = torch.nn.functional.interpolate(input, size=(target.size(2), target.size(3)), mode='bilinear',
+                                                align_corners=False)
     labels, nonzero = argmax_channels(target)                    # int_target, (tgt.sum() > 0)
     seg_loss, _ = lovasz.lovasz_segment_losses(input, labels, classes=[1], per_image=True, ignore=255)
     return _BinaryReduce.apply(seg_loss.reshape(-1), nonzero)
+
+
+binary_lovasz_loss_with_logits.accepts_lowres = True

@@ -119,3 +119,32 @@ def dice_from_cm(cm_per_image):
         check(lib.b200ssl_dice_from_cm(cm_per_image.data_ptr(), n, out.data_ptr(),
                                        stream_ptr(cm_per_image.device)), "dice_from_cm")
     return out
+
+
+def validation_dice(pred_logits, mask, threshold=0.5, fg_class=1, cm_out=None):
+    """The validation metric of train.py:171-175 in one pass over the mask:
+
+        one_hot = F.one_hot(argmax(pred_logits, 1), 2).permute(0, 3, 1, 2)
+        pred_map_binary = F.interpolate(one_hot, size=mask.shape[2:], mode='nearest')
+        metrics.dice_metric(pred_map_binary[:, 1:], (mask > 0.5)[:, 1:])
+
+    pred_logits: [N,C,h,w] fp32 at the network's resolution; mask: [N,Cm,H,W] fp32 (soft) labels.
+    Returns (dice [N] fp32 -- take .mean() for train.py:175 --, per-image 2x2 matrices [N,2,2] int64
+    {TN, FP; FN, TP}); `cm_out` accumulates into existing matrices."""
+    require_cuda(pred_logits, "pred_logits", torch.float32)
+    require_cuda(mask, "mask", torch.float32)
+    if pred_logits.dim() != 4 or mask.dim() != 4 or pred_logits.shape[0] != mask.shape[0]:
+        raise ValueError(f"pred_logits {tuple(pred_logits.shape)} / mask {tuple(mask.shape)} mismatch")
+    if not 0 <= fg_class < mask.shape[1]:
+        raise IndexError(f"class {fg_class} is not a channel of the mask")
+    pred_logits, mask = pred_logits.contiguous(), mask.contiguous()
+    n, c, h, w = pred_logits.shape
+    if cm_out is None:
+        cm_out = torch.zeros((n, 2, 2), dtype=torch.int64, device=mask.device)
+    elif tuple(cm_out.shape) != (n, 2, 2) or cm_out.dtype != torch.int64 or not cm_out.is_contiguous():
+        raise ValueError("cm_out must be a contiguous int64 tensor of shape [N,2,2]")
+    with torch.cuda.device(mask.device):
+        check(lib.b200ssl_validation_cm(pred_logits.data_ptr(), n, c, h, w, mask.data_ptr(), mask.shape[1],
+                                        mask.shape[2], mask.shape[3], float(threshold), int(fg_class),
+                                        cm_out.data_ptr(), stream_ptr(mask.device)), "validation_cm")
+    return dice_from_cm(cm_out), cm_out

@@ -321,3 +321,35 @@ def test_lovasz_from_logits_oracle_matches_reference(tag):
     ref = float(g[f"{tag}_loss"])
     assert abs(float(loss) - ref) <= 1e-5 * abs(ref)
     assert rel_l2(grad, g[f"{tag}_grad"]) <= 1e-5
+
+
+# ------------------------------------------------------- row N2 (student side) and the validation path
+def test_lowres_lovasz_oracle_vs_reference_golden():
+    """oracle.binary_lovasz_loss_lowres (up-sampling + loss + transposed interpolation) against vectors made by
+    the reference's losses.CalculateLoss + autograd (tests/golden/make_golden_lowres.py)."""
+    g = load_golden("lowres_lovasz")
+    for tag in ("s4", "s2", "ragged", "s8"):
+        loss, g_low, _ = oracle.binary_lovasz_loss_lowres(g[f"{tag}_low"], g[f"{tag}_target"].astype(np.float32),
+                                                           grad_out=0.7)
+        ref = g[f"{tag}_grad"]
+        assert abs(float(loss) * 0.7 - float(g[f"{tag}_loss"])) <= 1e-5 * abs(float(g[f"{tag}_loss"]))
+        assert np.linalg.norm(g_low - ref) <= 1e-5 * np.linalg.norm(ref)
+        assert not g_low[:, [c for c in range(g_low.shape[1]) if c != 1]].any()
+
+
+def test_upsample_backward_oracle_vs_autograd():
+    gen = torch.Generator().manual_seed(4)
+    for h, w, H, W in [(8, 8, 32, 32), (7, 9, 28, 36), (5, 5, 13, 17), (16, 16, 16, 16), (3, 4, 27, 20)]:
+        x = torch.randn(2, 3, h, w, generator=gen, requires_grad=True)
+        up = torch.randn(2, 3, H, W, generator=gen)
+        torch.nn.functional.interpolate(x, size=(H, W), mode="bilinear", align_corners=False).backward(up)
+        got = oracle.upsample_bilinear_backward(up.numpy(), (h, w))
+        assert np.linalg.norm(got - x.grad.numpy()) <= 1e-6 * np.linalg.norm(x.grad.numpy())
+
+
+def test_validation_dice_oracle_vs_reference_golden():
+    g = load_golden("validation")
+    for tag in ("v4", "vr", "v1"):
+        dice, cm = oracle.validation_dice(g[f"{tag}_pred"], g[f"{tag}_mask"])
+        assert np.array_equal(dice.view(np.uint32), g[f"{tag}_dice"].view(np.uint32))
+        assert int(cm.sum()) == g[f"{tag}_mask"].shape[0] * g[f"{tag}_mask"].shape[2] * g[f"{tag}_mask"].shape[3]
