@@ -108,35 +108,51 @@ __device__ __forceinline__ unsigned peer_poll(const PeerDev& c, unsigned seq, co
 // Block-cooperative: sums the world rows of step `seq` in the LOCAL mailbox in rank order (int64 adds for
 // counts, fp64 adds for scalars: identical bits on every rank) unless that step has been collected
 // already, then acknowledges the slot to every peer.  seq == 0: nothing has been posted yet.
+// One thread polls ONE (word, rank) pair, so the sys-scope loads of a chunk of blockDim.x pairs are in flight
+// together (a thread walking all ranks of an item one poll after the other costs 2*world dependent ~1 us
+// round trips: 16 at 8 GPUs); the sums then read the staged words from shared memory in rank order.
 __device__ __forceinline__ void peer_collect_block(const PeerDev& c, unsigned seq, int n_ints, int n_floats,
                                                    long long* __restrict__ ints_out, double* __restrict__ floats_out) {
   __shared__ unsigned s_done;
+  __shared__ unsigned s_words[256];
   unsigned long long* me = c.mail[c.rank];
   unsigned long long* status = me + kStatusOffset;
   if (threadIdx.x == 0) s_done = (unsigned)ld_sys(me + kCollectedOffset);
   __syncthreads();
   if (seq == 0u || (int)(s_done - seq) >= 0) return;   // block-uniform
   const int slot = (int)(seq % (unsigned)kPeerDepth);
+  const int world = c.world;
+  const int nw = 2 * n_ints + n_floats;                 // words per rank
+  const int per_chunk = (min((int)blockDim.x, 256) / world) & ~1;   // words per chunk (even: an int64 never straddles)
   bool dead = false;
-  for (int item = threadIdx.x; item < n_ints + n_floats; item += blockDim.x) {
-    if (item < n_ints) {
-      long long acc = 0;
-      for (int r = 0; r < c.world; ++r) {  // rank order: identical result on every rank
-        const unsigned lo = peer_poll(c, seq, me + ll_index(slot, r, 2 * item), status, &dead);
-        const unsigned hi = peer_poll(c, seq, me + ll_index(slot, r, 2 * item + 1), status, &dead);
-        acc += (long long)(((unsigned long long)hi << 32) | lo);
-      }
-      ints_out[item] = acc;
-    } else {
-      double acc = 0.0;
-      for (int r = 0; r < c.world; ++r)
-        acc += (double)__uint_as_float(peer_poll(c, seq, me + ll_index(slot, r, 2 * n_ints + (item - n_ints)), status, &dead));
-      floats_out[item - n_ints] = acc;
+  for (int w0 = 0; w0 < nw; w0 += per_chunk) {
+    const int words_here = min(per_chunk, nw - w0);
+    const int t = (int)threadIdx.x;
+    if (t < words_here * world) {
+      const int w = t / world, r = t - w * world;        // staged as [word][rank]
+      s_words[t] = peer_poll(c, seq, me + ll_index(slot, r, w0 + w), status, &dead);
     }
+    __syncthreads();
+    // one thread per item of this chunk: rank order, identical result on every rank
+    if (t < words_here) {
+      const int w = w0 + t;
+      if (w < 2 * n_ints) {
+        if ((w & 1) == 0) {
+          long long acc = 0;
+          for (int r = 0; r < world; ++r)
+            acc += (long long)(((unsigned long long)s_words[(t + 1) * world + r] << 32) | s_words[t * world + r]);
+          ints_out[w >> 1] = acc;
+        }
+      } else {
+        double acc = 0.0;
+        for (int r = 0; r < world; ++r) acc += (double)__uint_as_float(s_words[t * world + r]);
+        floats_out[w - 2 * n_ints] = acc;
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
   // every word of this slot has been consumed: tell the peers they may reuse it
-  if ((int)threadIdx.x < c.world) st_sys(c.mail[threadIdx.x] + kAckOffset + c.rank, (unsigned long long)seq);
+  if ((int)threadIdx.x < world) st_sys(c.mail[threadIdx.x] + kAckOffset + c.rank, (unsigned long long)seq);
   if (threadIdx.x == 0) st_sys(me + kCollectedOffset, (unsigned long long)seq);
 }
 
