@@ -331,11 +331,13 @@ def measure_step_config(b200ssl, cfg, args, rank, world, device, headline, clock
     # also completes the previous step's exchange -- no extra launch, no NCCL call on the data path.  If the box
     # cannot map peer memory every rank falls back to ONE torch.distributed all-reduce per step (collective choice).
     peer = reducer = None
-    if world > 1:
+    no_exchange = world > 1 and bool(os.environ.get("B200SSL_BENCH_NO_EXCHANGE"))   # diagnosis: per-GPU spread
+    if world > 1 and not no_exchange:
         peer = b200ssl.utils.make_peer_all_reduce(cfg["c"] * cfg["c"], 1, device)
         if peer is None:
             reducer = b200ssl.utils.StepReducer(cfg["c"], 1, device, backend="dist")
-    step = make_step(b200ssl, cfg, peer, static_outputs=True, ring=cfg["ring"])
+    use_graph = bool(os.environ.get("B200SSL_BENCH_GRAPH"))
+    step = make_step(b200ssl, cfg, peer, static_outputs=True, graph=use_graph, ring=cfg["ring"])
     step.bind_parameters(inp["params"], inp["ema_params"])     # like constructing an optimizer over the lists
     torch.manual_seed(0)            # the reference seeds every rank with 0 (distributed_trainer.py:17)
 
@@ -390,7 +392,10 @@ def measure_step_config(b200ssl, cfg, args, rank, world, device, headline, clock
     }
 
     # ---- multi-GPU: the exchange must have produced exactly what a library all-reduce produces ----
-    if world > 1:
+    if no_exchange:
+        res["collective"] = "NONE (B200SSL_BENCH_NO_EXCHANGE diagnosis run: independent replicas)"
+        res["region_ms_per_rank"] = per_rank_log[:6]
+    elif world > 1:
         out = one_step()
         if peer is not None:
             cm_sum, loss_sum = peer.result()

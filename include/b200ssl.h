@@ -470,12 +470,20 @@ int b200ssl_peer_destroy(b200ssl_peer_comm* comm);
 #define B200SSL_STEP_SOFTMAX 1
 #define B200SSL_STEP_SERIAL 1    /* flags: keep every kernel on `stream` (no internal fork/join) */
 #define B200SSL_STEP_PREFORKED 2 /* flags: the fork point was already recorded by b200ssl_loss_path_fork */
+/* A step issued in TWO calls, so that the chains that do not depend on the mask parameters are already
+ * running while the host still draws p / sigma and builds the taps: the first call (ISSUE_SIDE) forks and
+ * launches the Lovasz + confusion-matrix (+ peer exchange) and EMA chains on the internal side streams and
+ * returns without joining; the second call (ISSUE_MAIN, same descriptor with the mask/mix fields filled in)
+ * launches mask + mix on `stream` and joins the side streams back into it.  Every ISSUE_SIDE call must be
+ * followed by exactly one ISSUE_MAIN call on the same stream and device. */
+#define B200SSL_STEP_ISSUE_SIDE 4
+#define B200SSL_STEP_ISSUE_MAIN 8
 
 typedef struct b200ssl_step_desc {
   int32_t n, classes, h, w, image_channels, K, mode, cm_has_ignore;
   int64_t cm_ignore_index;
   int32_t cm_label_dtype;
-  int32_t flags;  /* B200SSL_STEP_SERIAL | B200SSL_STEP_PREFORKED */
+  int32_t flags;  /* B200SSL_STEP_SERIAL | B200SSL_STEP_PREFORKED | B200SSL_STEP_ISSUE_SIDE / _MAIN */
   b200ssl_lovasz_desc lovasz;
   /* inputs */
   const float* noise;      /* [n,1,h,w] */

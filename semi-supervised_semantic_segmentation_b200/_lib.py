@@ -49,7 +49,7 @@ class SgdHyper(C.Structure):
 _vp, _i, _i64, _sz, _d = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
 
 STEP_BINARY, STEP_SOFTMAX = 0, 1
-STEP_SERIAL, STEP_PREFORKED = 1, 2
+STEP_SERIAL, STEP_PREFORKED, STEP_ISSUE_SIDE, STEP_ISSUE_MAIN = 1, 2, 4, 8
 
 
 class StepDesc(C.Structure):

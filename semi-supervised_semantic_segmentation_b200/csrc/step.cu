@@ -57,17 +57,20 @@ static bool fused_front_end_ok(const b200ssl_step_desc* d, int64_t hw) {
          d->grad && hw <= (1ll << 28) && d->n <= 65535;
 }
 
+// which: bit 0 = the mask+mix chain, bit 1 = the side chains (Lovasz + matrix + peer exchange, EMA)
 static int loss_path_step_on(const b200ssl_step_desc* d, b200ssl_stream_t s_mix, b200ssl_stream_t s_lovasz,
-                             b200ssl_stream_t s_ema) {
+                             b200ssl_stream_t s_ema, int which) {
   using namespace b200ssl;
   const int64_t hw = (int64_t)d->h * d->w;
   int rc;
   bool posted = false;
   b200ssl_stream_t stream = s_mix;
+  const bool do_main = (which & 1) != 0, do_side = (which & 2) != 0;
 
   // 1.+2. mask and mix.  With images present the threshold pass is fused into the mix: the field S
   // and tau live in the cowmix workspace (S in its second region, tau behind the partials).
-  if (d->noise && d->image_a) {
+  if (!do_main) {
+  } else if (d->noise && d->image_a) {
     const size_t plane_bytes = align_up((size_t)d->n * hw * sizeof(float), 256);
     float* field = reinterpret_cast<float*>(static_cast<char*>(d->ws_cowmix) + plane_bytes);
     const size_t need = b200ssl_cowmix_workspace_bytes(d->n, d->h, d->w);
@@ -102,6 +105,7 @@ static int loss_path_step_on(const b200ssl_step_desc* d, b200ssl_stream_t s_mix,
       if (rc) return rc;
     }
   }
+  if (!do_side) return 0;
   // 3. Lovasz forward + backward with the upstream gradient small[2], 5. confusion matrix
   stream = s_lovasz;
   if (d->scores) {
@@ -194,24 +198,39 @@ extern "C" int b200ssl_loss_path_step(const b200ssl_step_desc* d, b200ssl_stream
   B200SSL_REQUIRE(d->n >= 1 && d->classes >= 1 && d->h >= 1 && d->w >= 1, "loss_path_step: bad extents");
   B200SSL_REQUIRE(d->mode == B200SSL_STEP_BINARY || d->mode == B200SSL_STEP_SOFTMAX, "loss_path_step: bad mode");
   cudaStream_t main = (cudaStream_t)stream;
-  const bool has_mix = d->noise || d->image_a, has_lov = d->scores != nullptr;
+  const bool only_side = (d->flags & B200SSL_STEP_ISSUE_SIDE) != 0, only_main = (d->flags & B200SSL_STEP_ISSUE_MAIN) != 0;
+  B200SSL_REQUIRE(!(only_side && only_main), "loss_path_step: ISSUE_SIDE and ISSUE_MAIN are two separate calls");
+  // a split step always has a mask+mix chain coming (that is what the second call issues)
+  const bool has_mix = d->noise || d->image_a || only_side, has_lov = d->scores != nullptr;
   const bool has_ema = d->ema_table && d->ema_entries > 0;
   const bool serial = (d->flags & B200SSL_STEP_SERIAL) != 0, preforked = (d->flags & B200SSL_STEP_PREFORKED) != 0;
-  SideStreams* ss = ((int)has_mix + (int)has_lov + (int)has_ema >= 2 && !serial) ? side_streams() : nullptr;
-  if (!ss) return loss_path_step_on(d, stream, stream, stream);
-  // fork: the side streams start after everything already queued on the caller's stream (or at the
-  // point recorded earlier by b200ssl_loss_path_fork)
-  if ((!preforked && cudaEventRecord(ss->fork, main) != cudaSuccess) ||
-      cudaStreamWaitEvent(ss->s[0], ss->fork, 0) != cudaSuccess ||
-      cudaStreamWaitEvent(ss->s[1], ss->fork, 0) != cudaSuccess) {
-    set_error("loss_path_step: fork failed: %s", cudaGetErrorString(cudaGetLastError()));
-    return (int)cudaErrorUnknown;
+  B200SSL_REQUIRE(!(serial && (only_side || only_main)), "loss_path_step: a split step cannot be serial");
+  SideStreams* ss = (((int)has_mix + (int)has_lov + (int)has_ema >= 2 || only_main) && !serial) ? side_streams() : nullptr;
+  if (!ss) {
+    B200SSL_REQUIRE(!(only_side || only_main), "loss_path_step: side streams unavailable for a split step");
+    return loss_path_step_on(d, stream, stream, stream, 3);
+  }
+  int rc = 0;
+  if (!only_main) {
+    // fork: the side streams start after everything already queued on the caller's stream (or at the
+    // point recorded earlier by b200ssl_loss_path_fork)
+    if ((!preforked && cudaEventRecord(ss->fork, main) != cudaSuccess) ||
+        cudaStreamWaitEvent(ss->s[0], ss->fork, 0) != cudaSuccess ||
+        cudaStreamWaitEvent(ss->s[1], ss->fork, 0) != cudaSuccess) {
+      set_error("loss_path_step: fork failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return (int)cudaErrorUnknown;
+    }
   }
   // Lovasz chain on the high-priority side stream, mask+mix on the caller's stream, EMA on the other
-  const int rc = loss_path_step_on(d, stream, ss->s[0], ss->s[1]);
+  if (only_side) {
+    rc = loss_path_step_on(d, stream, ss->s[0], ss->s[1], 2);
+    for (int i = 0; i < 2; ++i) cudaEventRecord(ss->join[i], ss->s[i]);   // joined by the ISSUE_MAIN call
+    return rc;
+  }
+  rc = loss_path_step_on(d, stream, ss->s[0], ss->s[1], only_main ? 1 : 3);
   // join (also on error paths, so that the caller's stream never runs ahead of the side work)
   for (int i = 0; i < 2; ++i) {
-    cudaEventRecord(ss->join[i], ss->s[i]);
+    if (!only_main) cudaEventRecord(ss->join[i], ss->s[i]);
     cudaStreamWaitEvent(main, ss->join[i], 0);
   }
   return rc;

@@ -280,14 +280,19 @@ class LossPathStep:
                     mixed_teacher = o["mixed_teacher"]
                     d.teacher_a, d.teacher_b, d.mixed_teacher = teacher_a.data_ptr(), teacher_b.data_ptr(), mixed_teacher.data_ptr()
                     out["mixed_teacher"] = mixed_teacher
-                if not self.serial and not use_graph:
-                    # fork point: the Lovasz / EMA chains need neither the mask parameters nor the noise
+                split = not self.serial and not use_graph
+                if split:
+                    # The Lovasz / matrix / exchange and EMA chains need neither the mask parameters nor the
+                    # noise: they are launched NOW (first half of the split step), so the GPU is already busy
+                    # while the host draws p / sigma and builds the taps (~0.1 ms) -- this is what a loop that
+                    # synchronises every step (loss.item()) sees as latency.
+                    d.flags |= _lib.STEP_ISSUE_SIDE
                     if current:
-                        check(lib.b200ssl_loss_path_fork(stream), "loss_path_fork")
+                        check(lib.b200ssl_loss_path_step(C.byref(d), stream), "loss_path_step (side chains)")
                     else:
                         with torch.cuda.device(dev):
-                            check(lib.b200ssl_loss_path_fork(stream), "loss_path_fork")
-                    d.flags |= _lib.STEP_PREFORKED
+                            check(lib.b200ssl_loss_path_step(C.byref(d), stream), "loss_path_step (side chains)")
+                    d.flags = (d.flags & ~_lib.STEP_ISSUE_SIDE) | _lib.STEP_ISSUE_MAIN
                 p, sigmas = cowmix.draw_mask_parameters(n, self.mask_proportion_range, self.sigma_range)
                 if self.static_outputs:
                     size = cowmix.stage_mask_parameters(p, sigmas, self._taps_dev)
