@@ -391,6 +391,13 @@ def measure_step_config(b200ssl, cfg, args, rank, world, device, headline, clock
         "lovasz": cfg["lovasz"], "gpu_launches_per_region": int(launches),
     }
 
+    if cfg["mode"] == "softmax":
+        # exact zero-delta tail pruning (csrc/lovasz.cu): share of the C*P (class, pixel) keys that had to be sorted
+        torch.cuda.synchronize(device)
+        ns = step._n_seg
+        sorted_keys = int(step._scratch["segi"][ns:2 * ns].sum())
+        res["lovasz_keys_sorted_fraction"] = round(sorted_keys / float(ns * P), 4)
+
     # ---- multi-GPU: the exchange must have produced exactly what a library all-reduce produces ----
     if no_exchange:
         res["collective"] = "NONE (B200SSL_BENCH_NO_EXCHANGE diagnosis run: independent replicas)"

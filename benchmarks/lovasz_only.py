@@ -15,11 +15,19 @@ from b200ssl import _lib  # noqa: E402
 
 def main():
     which = (sys.argv[1] if len(sys.argv) > 1 else "1,2,3").split(",")
+    scale = float(sys.argv[2]) if len(sys.argv) > 2 else None      # soft-max mode: probabilities of logits * scale
     dev = torch.device("cuda:0")
     out = {}
     for c in which:
         cfg = bench.CONFIGS[c]
         inp = bench.make_inputs(dev, 0, cfg=cfg)
+        if scale is not None and cfg["mode"] == "softmax":
+            gen = torch.Generator(device=dev).manual_seed(9)
+            logits = torch.randn(inp["scores"].shape, device=dev, generator=gen) * abs(scale)
+            if scale < 0:      # negative: logits that agree with the labels (a trained network)
+                logits += 12.0 * torch.nn.functional.one_hot(inp["target"], cfg["c"]).permute(0, 3, 1, 2)
+            inp["scores"] = torch.softmax(logits, 1)
+            del logits
         step = bench.make_step(b200ssl, cfg, None, serial=True, static_outputs=True, ring=1)
         for _ in range(3):
             step.lovasz_loss_and_grad(inp["scores"], inp["target"])

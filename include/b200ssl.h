@@ -149,7 +149,9 @@ int b200ssl_mix2_field(const float* a0, const float* b0, float* out0, int c0, co
  * Forward writes, per segment s:
  *   seg_loss[s]    fp32  dot(errors_sorted, lovasz_grad(fg_sorted))             (lovasz.py:200)
  *   seg_fg[s]      int32 number of valid foreground pixels (0 => absent class)   (lovasz.py:188)
- *   seg_valid[s]   int32 number of non-ignored pixels
+ *   seg_valid[s]   int32 number of non-ignored pixels that were sorted (all of them, except on the multi-class
+ *                  probability path, where background pixels behind the last foreground element -- error below
+ *                  min_fg |1 - p|, Jaccard delta exactly 0 -- are pruned before the sort)
  * and, for every pixel i of every summed class c, the unit gradient
  *   jgrad[n,c,i] = sign(p - fg) * (J[rank] - J[rank-1])      (0 for ignored pixels)
  * computed with the reference's fp32 operation sequence (integer counts -> IEEE div ->
