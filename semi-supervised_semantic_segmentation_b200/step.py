@@ -293,16 +293,24 @@ class LossPathStep:
                         with torch.cuda.device(dev):
                             check(lib.b200ssl_loss_path_step(C.byref(d), stream), "loss_path_step (side chains)")
                     d.flags = (d.flags & ~_lib.STEP_ISSUE_SIDE) | _lib.STEP_ISSUE_MAIN
-                p, sigmas = cowmix.draw_mask_parameters(n, self.mask_proportion_range, self.sigma_range)
-                if self.static_outputs:
-                    size = cowmix.stage_mask_parameters(p, sigmas, self._taps_dev)
-                    taps_dev = self._taps_dev
-                    noise = o["noise"]
-                    if not use_graph:
-                        noise.normal_()           # device generator, after the CPU draws (cowmix.py:44-55)
-                else:
-                    size, taps_dev = cowmix.upload_mask_parameters(p, sigmas, dev)
-                    noise = torch.normal(mean=0, std=1, size=(n, 1, h, w), dtype=torch.float32, device=dev)
+                try:
+                    p, sigmas = cowmix.draw_mask_parameters(n, self.mask_proportion_range, self.sigma_range)
+                    if self.static_outputs:
+                        size = cowmix.stage_mask_parameters(p, sigmas, self._taps_dev)
+                        taps_dev = self._taps_dev
+                        noise = o["noise"]
+                        if not use_graph:
+                            noise.normal_()           # device generator, after the CPU draws (cowmix.py:44-55)
+                    else:
+                        size, taps_dev = cowmix.upload_mask_parameters(p, sigmas, dev)
+                        noise = torch.normal(mean=0, std=1, size=(n, 1, h, w), dtype=torch.float32, device=dev)
+                except BaseException:
+                    if split:
+                        # the side chains of this step are already running: join them back into the caller's
+                        # stream (second half with no mask / mix work) before the error leaves this call
+                        with torch.cuda.device(dev):
+                            lib.b200ssl_loss_path_step(C.byref(d), stream)
+                    raise
                 d.K, d.image_channels = size, img_c
                 d.noise, d.taps, d.thr_factor = noise.data_ptr(), taps_dev.data_ptr(), taps_dev.data_ptr() + 4 * n * size
                 d.image_a, d.image_b = image_a.data_ptr(), image_b.data_ptr()
