@@ -214,13 +214,22 @@ def mix_case():
          out_special=ref_cowmix.mix_with_mask(a2, b2, mask).numpy())
 
 
+def reference_statements(path, first, last):
+    """Source lines first..last (1-based, inclusive) of a reference file, dedented: the reference's own statements,
+    compiled from the read-only tree at generation time (nothing is copied into this repository)."""
+    import textwrap
+    with open(path) as f:
+        lines = f.readlines()[first - 1:last]
+    return compile(textwrap.dedent("".join(lines)), f"{path}:{first}-{last}", "exec")
+
+
 def consistency_case():
-    """train.py:98-107 is inline code inside train() and train.py does not import here (kornia is not
-    installed), so these vectors come from executing the same ATen op sequence, line for line, as
-    restated in oracle/torch_port.confidence_masked_consistency -- the one golden file that is NOT
-    produced by a reference function."""
-    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
-    from oracle import torch_port
+    """train.py:97-108 is inline code inside train() and train.py does not import here (kornia is not installed).
+    Round 2: the golden no longer comes from the restated port -- the reference's OWN statements (those source
+    lines, compiled from /root/reference/train.py) are executed on seeded tensors, with `config` reduced to the one
+    key they read.  oracle/torch_port.confidence_masked_consistency is then checked against these vectors like
+    every other restatement (tests/test_oracle_golden.py)."""
+    code = reference_statements("/root/reference/train.py", 97, 108)
     gen = torch.Generator().manual_seed(53)
     n, c, h, w = 2, 3, 20, 28
     student = torch.randn(n, c, h, w, generator=gen) * 3
@@ -228,7 +237,10 @@ def consistency_case():
     out = dict(student=student.numpy(), teacher=teacher.numpy())
     for tag, thr in [("t097", 0.97), ("t06", 0.6)]:
         x = student.clone().requires_grad_(True)
-        loss, conf = torch_port.confidence_masked_consistency(x, teacher, thr)
+        ns = {"torch": torch, "mixed_ema_pred": teacher, "mixed_student_pred": x,
+              "config": {"train": {"confidence_threshold": thr}}}
+        exec(code, ns)
+        loss, conf = ns["consistency_loss"], ns["confidence_modulator"]
         loss.backward()
         out[f"{tag}_loss"], out[f"{tag}_conf"], out[f"{tag}_grad"] = loss.detach().numpy(), conf.numpy(), x.grad.numpy()
     save("consistency", **out)
