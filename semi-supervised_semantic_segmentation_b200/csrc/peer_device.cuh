@@ -108,13 +108,16 @@ __device__ __forceinline__ unsigned peer_poll(const PeerDev& c, unsigned seq, co
 // Block-cooperative: sums the world rows of step `seq` in the LOCAL mailbox in rank order (int64 adds for
 // counts, fp64 adds for scalars: identical bits on every rank) unless that step has been collected
 // already, then acknowledges the slot to every peer.  seq == 0: nothing has been posted yet.
-// One thread polls ONE (word, rank) pair, so the sys-scope loads of a chunk of blockDim.x pairs are in flight
-// together (a thread walking all ranks of an item one poll after the other costs 2*world dependent ~1 us
-// round trips: 16 at 8 GPUs); the sums then read the staged words from shared memory in rank order.
+// Every thread polls up to kPollUnroll (word, rank) pairs per round and ISSUES all of its sys-scope loads before it
+// looks at the first tag, so blockDim.x * kPollUnroll loads are in flight together (a thread walking all ranks of
+// an item one poll after the other costs 2*world dependent ~1 us round trips: 16 at 8 GPUs; one pair per thread
+// still cost 28 rounds for the 883 words x 8 ranks of a 21-class matrix: +57 us per step at N = 8).  The sums then
+// read the staged words from shared memory in rank order.
+constexpr int kPollUnroll = 8;
 __device__ __forceinline__ void peer_collect_block(const PeerDev& c, unsigned seq, int n_ints, int n_floats,
                                                    long long* __restrict__ ints_out, double* __restrict__ floats_out) {
   __shared__ unsigned s_done;
-  __shared__ unsigned s_words[256];
+  __shared__ unsigned s_words[256 * kPollUnroll];
   unsigned long long* me = c.mail[c.rank];
   unsigned long long* status = me + kStatusOffset;
   if (threadIdx.x == 0) s_done = (unsigned)ld_sys(me + kCollectedOffset);
@@ -122,30 +125,44 @@ __device__ __forceinline__ void peer_collect_block(const PeerDev& c, unsigned se
   if (seq == 0u || (int)(s_done - seq) >= 0) return;   // block-uniform
   const int slot = (int)(seq % (unsigned)kPeerDepth);
   const int world = c.world;
+  const int nthreads = min((int)blockDim.x, 256);
   const int nw = 2 * n_ints + n_floats;                 // words per rank
-  const int per_chunk = (min((int)blockDim.x, 256) / world) & ~1;   // words per chunk (even: an int64 never straddles)
+  const int per_chunk = ((nthreads * kPollUnroll) / world) & ~1;   // words per chunk (even: an int64 never straddles)
   bool dead = false;
+  const int t = (int)threadIdx.x;
   for (int w0 = 0; w0 < nw; w0 += per_chunk) {
     const int words_here = min(per_chunk, nw - w0);
-    const int t = (int)threadIdx.x;
-    if (t < words_here * world) {
-      const int w = t / world, r = t - w * world;        // staged as [word][rank]
-      s_words[t] = peer_poll(c, seq, me + ll_index(slot, r, w0 + w), status, &dead);
+    const int pairs_here = words_here * world;           // staged as [word][rank]
+    if (t < nthreads) {
+      unsigned long long v[kPollUnroll];
+#pragma unroll
+      for (int u = 0; u < kPollUnroll; ++u) {
+        const int idx = t + u * nthreads;
+        if (idx < pairs_here) v[u] = ld_sys(me + ll_index(slot, idx % world, w0 + idx / world));
+      }
+#pragma unroll
+      for (int u = 0; u < kPollUnroll; ++u) {
+        const int idx = t + u * nthreads;
+        if (idx < pairs_here)
+          s_words[idx] = ((unsigned)(v[u] >> 32) == seq)
+                             ? (unsigned)v[u]
+                             : peer_poll(c, seq, me + ll_index(slot, idx % world, w0 + idx / world), status, &dead);
+      }
     }
     __syncthreads();
     // one thread per item of this chunk: rank order, identical result on every rank
-    if (t < words_here) {
-      const int w = w0 + t;
+    for (int k = t; k < words_here; k += (int)blockDim.x) {
+      const int w = w0 + k;
       if (w < 2 * n_ints) {
         if ((w & 1) == 0) {
           long long acc = 0;
           for (int r = 0; r < world; ++r)
-            acc += (long long)(((unsigned long long)s_words[(t + 1) * world + r] << 32) | s_words[t * world + r]);
+            acc += (long long)(((unsigned long long)s_words[(k + 1) * world + r] << 32) | s_words[k * world + r]);
           ints_out[w >> 1] = acc;
         }
       } else {
         double acc = 0.0;
-        for (int r = 0; r < world; ++r) acc += (double)__uint_as_float(s_words[t * world + r]);
+        for (int r = 0; r < world; ++r) acc += (double)__uint_as_float(s_words[k * world + r]);
         floats_out[w - 2 * n_ints] = acc;
       }
     }
@@ -178,5 +195,11 @@ int binary_lovasz_fused_impl(const float* scores, const float* target, int n_ima
                              int32_t* seg_valid, float* grad, long long* cm, int cm_has_ignore,
                              int64_t cm_ignore_index, void* workspace, size_t workspace_bytes,
                              b200ssl_stream_t stream, const PeerTail* tail);                   // lovasz.cu
+
+int lovasz_forward_backward_tail(const b200ssl_lovasz_desc* d, const float* probas, const void* labels,
+                                 const float* grad_out, const int32_t* binary_nonzero, float* loss_out,
+                                 float* denom_out, float* seg_loss, int32_t* seg_fg, int32_t* seg_valid,
+                                 float* grad_probas, void* workspace, size_t workspace_bytes, b200ssl_stream_t stream,
+                                 const PeerTail* tail);                                        // lovasz.cu
 
 }  // namespace b200ssl

@@ -83,6 +83,31 @@ def main():
     assert step_g.graph_captures < 12 * 2
     peer_g.status()
     peer_g.close()
+    # soft-max mode (lovasz_softmax over 5 classes): the matrix kernel runs first and the Lovasz finalising block
+    # posts the 25 counts + the loss
+    c5 = 5
+    probas = torch.softmax(torch.randn(n, c5, h, w, generator=g) * 2, 1).to(dev)
+    labels5 = torch.randint(0, c5, (n, h, w), generator=g).to(dev)
+    tea5 = [torch.randn(n, c5, h, w, generator=g).to(dev) for _ in range(2)]
+    peer_s = b200ssl.utils.PeerAllReduce(c5 * c5, 1, dev)
+    step_s = b200ssl.LossPathStep(num_classes=c5, sigma_range=(2, 4), mode="softmax", peer=peer_s, static_outputs=True)
+    last = None
+    for it in range(7):
+        out = step_s(img[0], img[1], tea5[0], tea5[1], probas, labels5, params, ema)
+        want_cm = out["cm"].clone()
+        want_loss = out["loss"].double().reshape(1).clone()
+        dist.all_reduce(want_cm)
+        dist.all_reduce(want_loss)
+        torch.cuda.synchronize(dev)
+        if last is not None:
+            assert torch.equal(last[0], last[1]), rank          # completed by this step's post
+            assert torch.allclose(last[2].reshape(1), last[3], rtol=1e-15, atol=0), rank
+        last = (out["cm_sum"], want_cm, out["loss_sum"], want_loss)
+    peer_s.result()
+    torch.cuda.synchronize(dev)
+    assert torch.equal(last[0], last[1]) and torch.allclose(last[2].reshape(1), last[3], rtol=1e-15, atol=0), rank
+    peer_s.status()
+    peer_s.close()
     red.peer.close()
     dist.barrier()
     if rank == 0:
