@@ -181,7 +181,7 @@ def stage_of(kernel):
     return "other"
 
 
-def stage_algorithmic_bytes(P, C, n_params, fused_mask_mix):
+def stage_algorithmic_bytes(P, C, n_params):
     """SURVEY 8(d) per pixel: mask 8 (noise in, mask out), mix 40+12C (both tensors, one mask read),
     Lovasz fwd+bwd 8C+8 (scores in, gradient out, labels), confusion matrix 16 (int64 label + int64
     prediction); EMA 12 B per parameter.  The radix passes' own traffic is NOT algorithmic."""
@@ -296,7 +296,7 @@ def kernel_stage_table(b200ssl, cfg, inp, device, prof_steps, P, n_params, peak)
         st = stages.setdefault(stage_of(name), {"ms_per_step": 0.0, "kernels": []})
         st["ms_per_step"] += per_step
         st["kernels"].append(name)
-    abytes = stage_algorithmic_bytes(P, cfg["c"], n_params, True)
+    abytes = stage_algorithmic_bytes(P, cfg["c"], n_params)
     if "mix" in stages:
         stages["mix"]["note"] = "the fused threshold+mix kernel also writes the mask (4 of the mask stage's 8 B/px)"
     if "cm" not in stages and "lovasz" in stages and cfg["mode"] == "binary":
