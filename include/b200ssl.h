@@ -324,6 +324,14 @@ int b200ssl_lovasz_forward_logits(const b200ssl_lovasz_desc* d, const float* log
 int b200ssl_softmax_backward(const float* logits, const float* softmax_max, const float* softmax_sum, float* grad,
                              int n, int c, int64_t hw, b200ssl_stream_t stream);
 
+/* Round 2: the soft-max written out once, probas[n,C,hw] = exp(x - max) / sum (the arithmetic of softmax_stats + the
+ * logits key-build), and its backward from the stored probabilities, grad <- (grad - sum_c grad_c p_c) * p in place.
+ * With the exact tail pruning on the probability path, soft-max -> b200ssl_lovasz_forward -> this backward is faster
+ * than the never-materialising b200ssl_lovasz_forward_logits route (0.58 vs 0.94 ms at 4x21x512x512) at the price of
+ * one [n,C,hw] tensor kept for the backward pass. */
+int b200ssl_softmax_forward(const float* logits, int n, int c, int64_t hw, float* probas, b200ssl_stream_t stream);
+int b200ssl_softmax_backward_probas(const float* probas, float* grad, int n, int c, int64_t hw, b200ssl_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Row N2: bilinear up-sampling (F.interpolate(..., mode='bilinear', align_corners=False), train.py:
  * 71-75,93-94, losses.py:18-19) fused into the mix.  b200ssl_mix2_upsampled is b200ssl_mix2 /

@@ -109,6 +109,8 @@ SIGNATURES = {
     "b200ssl_softmax_stats": (_i, [_vp, _i, _i, _i64, _vp, _vp, _vp]),
     "b200ssl_lovasz_forward_logits": (_i, [C.POINTER(LovaszDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200ssl_softmax_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i64, _vp]),
+    "b200ssl_softmax_forward": (_i, [_vp, _i, _i, _i64, _vp, _vp]),
+    "b200ssl_softmax_backward_probas": (_i, [_vp, _vp, _i, _i, _i64, _vp]),
     "b200ssl_mix2_upsampled": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     "b200ssl_upsample_bilinear": (_i, [_vp, _i64, _i, _i, _vp, _i, _i, _vp]),
     "b200ssl_upsample_bilinear_backward": (_i, [_vp, _i64, _i, _i, _vp, _i, _i, _vp]),

@@ -179,6 +179,92 @@ softmax_backward_reg_kernel(const float* __restrict__ x, const float* __restrict
   }
 }
 
+// ---- round 2: F.softmax written out once + the backward from the stored probabilities.  With the exact tail
+//      pruning and the one-byte label copy on the probability path, `soft-max -> lovasz_softmax -> soft-max
+//      backward` through these two kernels (8C + 12C bytes per pixel) beats the never-materialising logits
+//      front end above (0.58 vs 0.94 ms at 4x21x512x512); lovasz_softmax_with_logits takes this route by default.
+//      p = exp(x - max) / sum exactly as softmax_stats + the logits key-build form it.
+__global__ void __launch_bounds__(kSmThreads)
+softmax_forward_reg_kernel(const float* __restrict__ x, int n, int C, long long hw, float* __restrict__ probas) {
+  const long long total = (long long)n * hw;
+  for (long long q = (long long)blockIdx.x * kSmThreads + threadIdx.x; q < total; q += (long long)gridDim.x * kSmThreads) {
+    const long long img = q / hw;
+    const long long off = q - img * hw;
+    const float* base = x + img * C * hw + off;
+    float* out = probas + img * C * hw + off;
+    float v[kSmRegC];
+#pragma unroll
+    for (int c = 0; c < kSmRegC; ++c) v[c] = (c < C) ? ld_stream_f1(base + (long long)c * hw) : -INFINITY;
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < kSmRegC; ++c)
+      if (c < C) m = (v[c] > m || v[c] != v[c]) ? v[c] : m;
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < kSmRegC; ++c)
+      if (c < C) {
+        v[c] = expf(__fsub_rn(v[c], m));
+        s = __fadd_rn(s, v[c]);
+      }
+#pragma unroll
+    for (int c = 0; c < kSmRegC; ++c)
+      if (c < C) out[(long long)c * hw] = __fdiv_rn(v[c], s);
+  }
+}
+
+// generic C: three sweeps over the channels of a pixel (max, sum, write); the planes of one pixel column stay in L1/L2
+__global__ void __launch_bounds__(kSmThreads)
+softmax_forward_kernel(const float* __restrict__ x, int n, int C, long long hw, float* __restrict__ probas) {
+  const long long total = (long long)n * hw;
+  for (long long q = (long long)blockIdx.x * kSmThreads + threadIdx.x; q < total; q += (long long)gridDim.x * kSmThreads) {
+    const long long img = q / hw;
+    const long long off = q - img * hw;
+    const float* base = x + img * C * hw + off;
+    float* out = probas + img * C * hw + off;
+    float m = -INFINITY;
+    for (int c = 0; c < C; ++c) {
+      const float v = __ldg(base + (long long)c * hw);
+      m = (v > m || v != v) ? v : m;
+    }
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = __fadd_rn(s, expf(__fsub_rn(__ldg(base + (long long)c * hw), m)));
+    for (int c = 0; c < C; ++c) out[(long long)c * hw] = __fdiv_rn(expf(__fsub_rn(__ldg(base + (long long)c * hw), m)), s);
+  }
+}
+
+// grad <- (grad - sum_c grad_c p_c) * p, in place, p read from the stored probabilities
+template <bool REG>
+__global__ void __launch_bounds__(kSmThreads)
+softmax_backward_probas_kernel(const float* __restrict__ probas, float* grad, int n, int C, long long hw) {
+  const long long total = (long long)n * hw;
+  for (long long q = (long long)blockIdx.x * kSmThreads + threadIdx.x; q < total; q += (long long)gridDim.x * kSmThreads) {
+    const long long img = q / hw;
+    const long long off = q - img * hw;
+    const float* pb = probas + img * C * hw + off;
+    float* gb = grad + img * C * hw + off;
+    if (REG) {
+      float pr[kSmRegC], g[kSmRegC];
+#pragma unroll
+      for (int c = 0; c < kSmRegC; ++c) {
+        pr[c] = (c < C) ? ld_stream_f1(pb + (long long)c * hw) : 0.f;
+        g[c] = (c < C) ? gb[(long long)c * hw] : 0.f;
+      }
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < kSmRegC; ++c)
+        if (c < C) dot = __fadd_rn(dot, __fmul_rn(g[c], pr[c]));
+#pragma unroll
+      for (int c = 0; c < kSmRegC; ++c)
+        if (c < C) gb[(long long)c * hw] = __fmul_rn(__fsub_rn(g[c], dot), pr[c]);
+    } else {
+      float dot = 0.f;
+      for (int c = 0; c < C; ++c) dot = __fadd_rn(dot, __fmul_rn(gb[(long long)c * hw], __ldg(pb + (long long)c * hw)));
+      for (int c = 0; c < C; ++c)
+        gb[(long long)c * hw] = __fmul_rn(__fsub_rn(gb[(long long)c * hw], dot), __ldg(pb + (long long)c * hw));
+    }
+  }
+}
+
 static int sm_grid(long long work) {
   long long blocks = (work + kSmThreads - 1) / kSmThreads;
   const long long cap = (long long)kNumSMs * 8 * 16;
@@ -217,6 +303,30 @@ int b200ssl_softmax_backward(const float* logits, const float* softmax_max, cons
   else if (vec) softmax_backward_kernel<4><<<sm_grid((long long)n * hw / 4), kSmThreads, 0, s>>>(logits, softmax_max, softmax_sum, grad, n, c, hw);
   else softmax_backward_kernel<1><<<sm_grid((long long)n * hw), kSmThreads, 0, s>>>(logits, softmax_max, softmax_sum, grad, n, c, hw);
   return check_launch("softmax_backward");
+}
+
+int b200ssl_softmax_forward(const float* logits, int n, int c, int64_t hw, float* probas, b200ssl_stream_t stream) {
+  using namespace b200ssl;
+  B200SSL_REQUIRE(n >= 0 && c >= 1 && hw >= 0, "softmax_forward: bad extents");
+  if (n == 0 || hw == 0) return 0;
+  B200SSL_REQUIRE(logits && probas, "softmax_forward: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  prof_begin("softmax_forward", s);
+  if (c <= kSmRegC) softmax_forward_reg_kernel<<<sm_grid((long long)n * hw), kSmThreads, 0, s>>>(logits, n, c, hw, probas);
+  else softmax_forward_kernel<<<sm_grid((long long)n * hw), kSmThreads, 0, s>>>(logits, n, c, hw, probas);
+  return check_launch("softmax_forward");
+}
+
+int b200ssl_softmax_backward_probas(const float* probas, float* grad, int n, int c, int64_t hw, b200ssl_stream_t stream) {
+  using namespace b200ssl;
+  B200SSL_REQUIRE(n >= 0 && c >= 1 && hw >= 0, "softmax_backward_probas: bad extents");
+  if (n == 0 || hw == 0) return 0;
+  B200SSL_REQUIRE(probas && grad, "softmax_backward_probas: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  prof_begin("softmax_backward_probas", s);
+  if (c <= kSmRegC) softmax_backward_probas_kernel<true><<<sm_grid((long long)n * hw), kSmThreads, 0, s>>>(probas, grad, n, c, hw);
+  else softmax_backward_probas_kernel<false><<<sm_grid((long long)n * hw), kSmThreads, 0, s>>>(probas, grad, n, c, hw);
+  return check_launch("softmax_backward_probas");
 }
 
 }  // extern "C"

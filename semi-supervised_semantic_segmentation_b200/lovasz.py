@@ -213,10 +213,65 @@ class _LovaszFromLogits(torch.autograd.Function):
         return grad, None, None
 
 
-def lovasz_softmax_with_logits(logits, labels, classes='present', per_image=False, ignore=None):
+class _LovaszViaProbas(torch.autograd.Function):
+    """logits -> lovasz_softmax(F.softmax(logits, 1), labels) with the soft-max written out ONCE by
+    b200ssl_softmax_forward and the loss taken on the probability path (exact tail pruning, one-byte label copy);
+    backward = segment scales, then b200ssl_softmax_backward_probas in place.  Faster than the never-materialising
+    route above (0.58 vs 0.94 ms at 4x21x512x512) for one [N,C,H,W] tensor kept until the backward pass."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, desc):
+        dev = logits.device
+        n, c = logits.shape[0], logits.shape[1]
+        hw = logits[0, 0].numel()
+        n_seg = lib.b200ssl_lovasz_num_segments(C.byref(desc))
+        if n_seg < 0:
+            check(n_seg, "lovasz_num_segments")
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        seg_loss = torch.empty(max(n_seg, 1), dtype=torch.float32, device=dev)
+        seg_meta = torch.empty((2, max(n_seg, 1)), dtype=torch.int32, device=dev)
+        probas = torch.empty_like(logits)
+        jgrad = torch.empty_like(logits)
+        ws = _lib.workspaces.get(dev, "lovasz", lib.b200ssl_lovasz_workspace_bytes(C.byref(desc)))
+        with torch.cuda.device(dev):
+            st = stream_ptr(dev)
+            check(lib.b200ssl_softmax_forward(logits.data_ptr(), n, c, hw, probas.data_ptr(), st), "softmax_forward")
+            check(lib.b200ssl_lovasz_forward(
+                C.byref(desc), probas.data_ptr(), labels.data_ptr(), loss.data_ptr(), seg_loss.data_ptr(),
+                seg_meta[0].data_ptr(), seg_meta[1].data_ptr(), jgrad.data_ptr(), ws.data_ptr(), ws.numel(), st),
+                "lovasz_forward")
+        ctx.desc, ctx.n_seg = desc, n_seg
+        ctx.save_for_backward(probas, jgrad, seg_meta)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        probas, jgrad, seg_meta = ctx.saved_tensors
+        dev = probas.device
+        desc, n_seg = ctx.desc, ctx.n_seg
+        n, c = probas.shape[0], probas.shape[1]
+        hw = probas[0, 0].numel()
+        with torch.cuda.device(dev):
+            st = stream_ptr(dev)
+            g_loss = g_loss.to(torch.float32).contiguous()
+            scale = torch.empty(max(n_seg, 1), dtype=torch.float32, device=dev)
+            check(lib.b200ssl_lovasz_seg_scale(C.byref(desc), g_loss.data_ptr(), seg_meta[0].data_ptr(),
+                                               seg_meta[1].data_ptr(), scale.data_ptr(), st), "lovasz_seg_scale")
+            grad = torch.empty_like(jgrad)
+            check(lib.b200ssl_lovasz_backward(C.byref(desc), scale.data_ptr(), jgrad.data_ptr(), grad.data_ptr(), st),
+                  "lovasz_backward")
+            check(lib.b200ssl_softmax_backward_probas(probas.data_ptr(), grad.data_ptr(), n, c, hw, st),
+                  "softmax_backward_probas")
+        return grad, None, None
+
+
+def lovasz_softmax_with_logits(logits, labels, classes='present', per_image=False, ignore=None, materialize=True):
     """`lovasz_softmax(F.softmax(logits, dim=1), labels, classes, per_image, ignore)` (lovasz.py:155-160's
     contract: "probas ... typically the output of a softmax") computed from the logits; the gradient flows
-    to the logits.  Same degenerate-input behaviour as `lovasz_softmax`."""
+    to the logits.  Same degenerate-input behaviour as `lovasz_softmax`.
+    materialize=True (default, faster): the probabilities are written once into a scratch tensor that lives
+    until the backward pass; materialize=False: they are formed in registers inside the key-build and never
+    stored (two [N,H,W] statistics planes instead of one [N,C,H,W] tensor)."""
     logits, labels = _prepare(logits, labels)
     if logits.shape[1] < 2:
         raise ValueError("lovasz_softmax_with_logits needs at least 2 channels (use lovasz_softmax for sigmoid outputs)")
@@ -227,7 +282,7 @@ def lovasz_softmax_with_logits(logits, labels, classes='present', per_image=Fals
             return 0
         return logits.permute(0, 2, 3, 1).reshape(-1, logits.shape[1]) * 0.
     desc = _make_desc(logits, labels, classes, per_image, ignore)
-    return _LovaszFromLogits.apply(logits, labels, desc)
+    return (_LovaszViaProbas if materialize else _LovaszFromLogits).apply(logits, labels, desc)
 
 
 # --------------------------- IoU helpers (lovasz.py:34-73), from the confusion matrix -----------

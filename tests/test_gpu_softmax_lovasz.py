@@ -19,14 +19,16 @@ def ssl():
     return b200ssl
 
 
+@pytest.mark.parametrize("materialize", [True, False])
 @pytest.mark.parametrize("tag", list(SOFTMAX_LOVASZ_CASES))
-def test_from_logits_matches_reference_golden(ssl, tag):
+def test_from_logits_matches_reference_golden(ssl, tag, materialize):
     dev = torch.device("cuda:0")
     g = load_golden("softmax_lovasz")
     classes, per_image, ignore = SOFTMAX_LOVASZ_CASES[tag]
     x = torch.from_numpy(g[f"{tag}_logits"]).to(dev).requires_grad_(True)
     labels = torch.from_numpy(g[f"{tag}_labels"]).to(dev)
-    loss = ssl.lovasz.lovasz_softmax_with_logits(x, labels, classes=classes, per_image=per_image, ignore=ignore)
+    loss = ssl.lovasz.lovasz_softmax_with_logits(x, labels, classes=classes, per_image=per_image, ignore=ignore,
+                                                 materialize=materialize)
     loss.backward()
     ref = float(g[f"{tag}_loss"])
     assert abs(float(loss) - ref) <= 1e-5 * abs(ref)
@@ -44,9 +46,10 @@ def test_from_logits_matches_unfused_path_and_oracle(ssl, shape, label_dtype):
     blob = torch.nn.functional.avg_pool2d(torch.randn(n, c, h, w, generator=gen), 9, 1, 4)
     labels = blob.argmax(1)
     labels[torch.rand(n, h, w, generator=gen) < 0.05] = 255
-    for per_image in (False, True):
+    for per_image, materialize in ((False, True), (True, True), (False, False), (True, False)):
         x = logits.to(dev).requires_grad_(True)
-        loss = ssl.lovasz.lovasz_softmax_with_logits(x, labels.to(dev).to(label_dtype), per_image=per_image, ignore=255)
+        loss = ssl.lovasz.lovasz_softmax_with_logits(x, labels.to(dev).to(label_dtype), per_image=per_image, ignore=255,
+                                                     materialize=materialize)
         loss.backward()
         y = logits.to(dev).requires_grad_(True)
         loss2 = ssl.lovasz.lovasz_softmax(torch.softmax(y, 1), labels.to(dev).to(label_dtype), per_image=per_image, ignore=255)
@@ -80,3 +83,10 @@ def test_softmax_stats_and_backward_kernels(ssl):
         _lib.check(_lib.lib.b200ssl_softmax_backward(x.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
                                                      got.data_ptr(), n, c, hw, st))
         assert rel_l2(got.cpu().numpy(), want.cpu().numpy()) <= 1e-6
+        # round 2: the soft-max written out, and its backward from the stored probabilities
+        probas = torch.empty_like(x)
+        _lib.check(_lib.lib.b200ssl_softmax_forward(x.data_ptr(), n, c, hw, probas.data_ptr(), st))
+        assert torch.allclose(probas, p, rtol=2e-6, atol=1e-30)
+        got2 = g.clone()
+        _lib.check(_lib.lib.b200ssl_softmax_backward_probas(probas.data_ptr(), got2.data_ptr(), n, c, hw, st))
+        assert rel_l2(got2.cpu().numpy(), want.cpu().numpy()) <= 1e-6
