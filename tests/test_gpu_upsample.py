@@ -47,7 +47,9 @@ def test_upsample_and_fused_mix_match_golden(ssl, tag):
 
 
 @pytest.mark.parametrize("shape", [(2, 2, 128, 128, 512, 512), (1, 19, 64, 128, 256, 512), (3, 2, 31, 45, 97, 131),
-                                   (1, 1, 1, 1, 7, 9), (2, 3, 40, 40, 40, 40)])
+                                   (1, 1, 1, 1, 7, 9), (2, 3, 40, 40, 40, 40),
+                                   # exact stride 4 (the constant-tap path) down to one- and two-column inputs
+                                   (1, 2, 1, 1, 4, 4), (2, 3, 2, 3, 8, 12), (1, 1, 5, 2, 20, 8), (1, 4, 33, 65, 132, 260)])
 def test_upsample_matches_oracle_and_torch_cuda(ssl, shape):
     dev = torch.device("cuda:0")
     n, c, h, w, H, W = shape
