@@ -225,6 +225,145 @@ confusion_kernel(const T* __restrict__ labels, const T* __restrict__ preds, long
   }
 }
 
+// ---- uint8 labels: 16 pixels per lane, runs merged ACROSS the lanes of a warp ------------------------
+// A warp step covers 512 consecutive pixels; on segmentation masks that is one to a few dozen runs of equal
+// (label, pred) pairs, and the kernel is bound by the instructions it issues per pixel (ncu r2_u: 71 % issue
+// utilisation with the first version of this kernel), then by shared-memory atomics (about 2 LSU cycles per
+// active lane), not by HBM.  So: every lane finds the boundaries inside its 16 pixels with byte arithmetic
+// (pixel i differs from pixel i-1; one dot-product instruction per word packs the flags into a 16-bit mask),
+// which gives its first run (key kf, length cf) and its last run (kt, ct); a lane without a boundary is one run
+// of 16.  Runs are then stitched across lanes with two ballots and one shuffle: the lane in which a run STARTS
+// adds the whole run -- its own tail, 16 for every following boundary-free lane that continues it, and the head
+// of the lane the run ends in -- with ONE atomic.  Runs that start and end inside a lane (two or more
+// boundaries in 16 pixels) are added by that lane directly.  Exact integer counts, bit-identical to the generic
+// kernel.  A key is the byte quadruple [label, pred, pred, pred] (one PRMT to build, two to compare/decode).
+__device__ __forceinline__ unsigned nonzero_bytes_x128(unsigned d) {   // byte i = (byte i of d != 0) ? 0x80 : 0
+  return (((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d) & 0x80808080u;
+}
+
+__device__ __forceinline__ unsigned byte_of(const unsigned (&w)[4], int pixel) {
+  const unsigned lo = pixel < 4 ? w[0] : w[1], hi = pixel < 12 ? w[2] : w[3];
+  return ((pixel < 8 ? lo : hi) >> ((pixel & 3) * 8)) & 0xffu;
+}
+
+__device__ __forceinline__ void smem_red_add(unsigned addr, unsigned v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// SIMPLE: no other bucket, no dropped counter and the void label (if any) is not a class index, so a pixel is
+// counted iff max(label, pred) < C.  n_vec = plane_pixels / 16 (< 2^31, checked by the launcher).
+template <int UNROLL, bool SIMPLE>
+__global__ void __launch_bounds__(kCmThreads)
+confusion_u8_kernel(const unsigned char* __restrict__ labels, const unsigned char* __restrict__ preds,
+                    long long plane_pixels, int n_vec, int C, int D, bool has_ignore, int ignore32, int copies,
+                    unsigned long long* __restrict__ cm, long long cm_plane_stride,
+                    unsigned long long* __restrict__ dropped_out) {
+  extern __shared__ unsigned smem_hist[];
+  const int bins = D * D;
+  labels += (long long)blockIdx.y * plane_pixels;
+  preds += (long long)blockIdx.y * plane_pixels;
+  cm += (long long)blockIdx.y * cm_plane_stride;
+  for (int i = threadIdx.x; i < copies * bins; i += blockDim.x) smem_hist[i] = 0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  const int lane = (int)lane_id();
+  const unsigned hist_addr = (unsigned)__cvta_generic_to_shared(smem_hist + (warp % copies) * bins);
+  unsigned dropped = 0;
+  auto add = [&](unsigned key, unsigned count) {
+    const unsigned l = key & 0xffu, p = key >> 24;
+    if (SIMPLE) {
+      if (max(l, p) < (unsigned)C) smem_red_add(hist_addr + (l * D + p) * 4u, count);
+    } else {
+      unsigned d1 = 0;
+      const int b = make_bin32((int)l, (int)p, C, D, has_ignore, ignore32, d1);
+      dropped += d1 * count;
+      if (b >= 0) smem_red_add(hist_addr + (unsigned)b * 4u, count);
+    }
+  };
+
+  const int n_groups = (int)((plane_pixels + 511) >> 9);
+  const int per_block = (n_groups + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int g_begin = (int)min((long long)blockIdx.x * per_block, (long long)n_groups);
+  const int g_end = min(n_groups, g_begin + per_block);
+  const uint4* __restrict__ lvec = reinterpret_cast<const uint4*>(labels);
+  const uint4* __restrict__ pvec = reinterpret_cast<const uint4*>(preds);
+  for (int g0 = g_begin + warp; g0 < g_end; g0 += kCmWarps * UNROLL) {
+    uint4 lv[UNROLL], pv[UNROLL];
+    bool full[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int g = g0 + u * kCmWarps;
+      const int v = g * 32 + lane;
+      full[u] = (g < g_end) && (v < n_vec);
+      if (full[u]) {
+        lv[u] = ld_stream_u4(lvec + v);
+        pv[u] = ld_stream_u4(pvec + v);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int g = g0 + u * kCmWarps;
+      if (g >= g_end) break;  // warp-uniform
+      // a lane without a full vector: keys that link to nothing, and it is no continuation of anything
+      unsigned kf = 0x00ff0100u, kt = 0x00ff0200u, cf = 0, ct = 0;
+      bool uni = false;
+      if (full[u]) {
+        const unsigned lw[4] = {lv[u].x, lv[u].y, lv[u].z, lv[u].w};
+        const unsigned pw[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w};
+        // byte i of bnd[w] != 0  <=>  pixel 4w+i differs from pixel 4w+i-1 (pixel 0: never)
+        unsigned bnd[4];
+        bnd[0] = (lw[0] ^ __byte_perm(lw[0], 0u, 0x2100)) | (pw[0] ^ __byte_perm(pw[0], 0u, 0x2100));
+#pragma unroll
+        for (int w = 1; w < 4; ++w)
+          bnd[w] = (lw[w] ^ __byte_perm(lw[w - 1], lw[w], 0x6543)) | (pw[w] ^ __byte_perm(pw[w - 1], pw[w], 0x6543));
+        const unsigned lo = __dp4a(nonzero_bytes_x128(bnd[0]), 0x08040201u,
+                                   __dp4a(nonzero_bytes_x128(bnd[1]), 0x80402010u, 0u));
+        const unsigned hi = __dp4a(nonzero_bytes_x128(bnd[2]), 0x08040201u,
+                                   __dp4a(nonzero_bytes_x128(bnd[3]), 0x80402010u, 0u));
+        const unsigned b16 = (lo + (hi << 8)) >> 7;             // bit i: a run starts at pixel i (i >= 1)
+        kf = __byte_perm(lw[0], pw[0], 0x4440);
+        kt = __byte_perm(lw[3], pw[3], 0x7773);
+        uni = b16 == 0u;
+        cf = (unsigned)(__ffs(b16 | 0x10000u) - 1);             // length of the first run (16: no boundary)
+        ct = (unsigned)(__clz(b16 | 1u) - 15);                  // 16 - position of the last boundary
+        unsigned inner = b16 & (b16 - 1u);
+        int pos = (int)cf;
+        while (inner) {                                         // runs that begin and end inside this lane
+          const int next = __ffs(inner) - 1;
+          add(byte_of(lw, pos) | (byte_of(pw, pos) << 24), (unsigned)(next - pos));
+          pos = next;
+          inner &= inner - 1u;
+        }
+      }
+      const unsigned prev_t = __shfl_up_sync(0xffffffffu, kt, 1);
+      const bool linked = lane > 0 && kf == prev_t;                  // my first run continues the previous lane's last
+      const unsigned U = __ballot_sync(0xffffffffu, uni), L = __ballot_sync(0xffffffffu, linked);
+      const unsigned above = lane == 31 ? 0u : (0xffffffffu << (lane + 1));
+      const unsigned stop = ~(L & U) & above;                        // first later lane that is not a pure continuation
+      const int e = stop ? (__ffs(stop) - 1) : 32;
+      const unsigned cf_e = __shfl_sync(0xffffffffu, cf, e & 31);
+      if (full[u]) {
+        if (!uni || !linked) {                                       // my last run starts in this lane
+          unsigned total = ct + 16u * (unsigned)(e - lane - 1);
+          if (e < 32 && ((L >> e) & 1u)) total += cf_e;              // ... and ends inside lane e
+          add(kt, total);
+        }
+        if (!uni && !linked) add(kf, cf);                            // a first run nobody else owns
+      } else if (g * 32 + lane == n_vec) {                           // ragged tail of the plane
+        const long long first = (long long)n_vec * 16;
+        for (int i = 0; first + i < plane_pixels; ++i)
+          add((unsigned)labels[first + i] | ((unsigned)preds[first + i] << 24), 1u);
+      }
+    }
+  }
+  if (!SIMPLE && dropped_out) {
+    const unsigned d = warp_sum(dropped);
+    if (lane == 0 && d) atomicAdd(dropped_out, (unsigned long long)d);
+  }
+  __syncthreads();
+  flush_hist(smem_hist, copies, bins, cm);
+}
+
 // ---- fused argmax + confusion matrix from logits -----------------------------------------------
 // logits [n_images, C, hw] fp32; each lane owns 4 consecutive pixels (float4 per channel).
 template <typename T>
@@ -351,6 +490,35 @@ static int launch_confusion(const void* labels, const void* preds, long long pla
   return check_launch("confusion_matrix");
 }
 
+constexpr int kCm8Unroll = 2;                     // 1: 2-5 % slower (r2_u), 4 in the first version: no gain
+constexpr long long kCm8MaxPlane = 1ll << 34;    // 32-bit vector indices inside confusion_u8_kernel
+
+static int launch_confusion_u8(const void* labels, const void* preds, long long plane_pixels, int planes, int C,
+                               int D, bool has_ignore, long long ignore, int copies, unsigned long long* cm,
+                               long long cm_stride, unsigned long long* dropped, cudaStream_t s) {
+  const size_t smem = (size_t)copies * D * D * 4;
+  const bool ign_fits = ignore >= 0 && ignore <= 255;               // no uint8 label equals any other value
+  const bool ign = has_ignore && ign_fits;
+  const bool simple = D == C && dropped == nullptr && (!ign || ignore >= C);
+  auto kern = simple ? confusion_u8_kernel<kCm8Unroll, true> : confusion_u8_kernel<kCm8Unroll, false>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // one wave: as many CTAs as fit at once, each with one contiguous range of the plane
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCmThreads, smem) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  const long long groups = (plane_pixels + 511) / 512;
+  long long bx = (groups + kCmWarps * kCm8Unroll - 1) / (kCmWarps * kCm8Unroll);
+  long long cap = (long long)kNumSMs * per_sm / planes;
+  if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  prof_begin("confusion_matrix", s);
+  kern<<<dim3((unsigned)bx, (unsigned)planes), kCmThreads, smem, s>>>(
+      static_cast<const unsigned char*>(labels), static_cast<const unsigned char*>(preds), plane_pixels,
+      (int)(plane_pixels >> 4), C, D, ign, ign ? (int)ignore : -1, copies, cm, cm_stride, dropped);
+  return check_launch("confusion_matrix");
+}
+
 }  // namespace b200ssl
 
 extern "C" {
@@ -390,6 +558,8 @@ int b200ssl_confusion_matrix(const void* labels, const void* preds, int64_t n_pi
       return vec ? launch_confusion<int, 4>(labels, preds, plane, planes, num_classes, D, has_ign, ignore_index, ucm, stride, udrop, s)
                  : launch_confusion<int, 1>(labels, preds, plane, planes, num_classes, D, has_ign, ignore_index, ucm, stride, udrop, s);
     case B200SSL_U8:
+      if (vec && cm_copies(D) > 0 && plane <= kCm8MaxPlane)
+        return launch_confusion_u8(labels, preds, plane, planes, num_classes, D, has_ign, ignore_index, cm_copies(D), ucm, stride, udrop, s);
       return vec ? launch_confusion<unsigned char, 16>(labels, preds, plane, planes, num_classes, D, has_ign, ignore_index, ucm, stride, udrop, s)
                  : launch_confusion<unsigned char, 1>(labels, preds, plane, planes, num_classes, D, has_ign, ignore_index, ucm, stride, udrop, s);
     default:

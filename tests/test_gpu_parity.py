@@ -424,6 +424,34 @@ def test_confusion_out_of_range_and_other_bucket(ssl, dev):
     assert np.array_equal(cmb.cpu().numpy(), ob)
 
 
+@pytest.mark.parametrize("run", [1, 3, 16, 17, 100, 5000])
+@pytest.mark.parametrize("n_pixels", [16 * 32 * 7, 100003, 15, 1 << 20])
+def test_confusion_uint8_run_stitching(ssl, dev, run, n_pixels):
+    """uint8 labels take the kernel that merges runs of equal (label, pred) pairs across the lanes of a warp:
+    run lengths around the 16 pixels of a lane and the 512 of a warp step, ragged ends, void labels, labels and
+    predictions outside [0, C) (dropped and counted, or the other bucket)."""
+    rng = np.random.default_rng(run * 7 + n_pixels % 1000)
+    c = 19
+
+    def runs(values):
+        out = np.empty(0, np.uint8)
+        while out.size < n_pixels:
+            k = max(1, int(n_pixels / max(run, 1) / 4) + 1)
+            out = np.concatenate([out, np.repeat(rng.choice(values, k).astype(np.uint8), rng.integers(1, 2 * run + 1, k))])
+        return out[:n_pixels]
+
+    labels = runs(np.array(list(range(c)) + [255, 255, 30]))
+    preds = np.where(rng.random(n_pixels) < 0.5, labels, runs(np.array(list(range(c)) + [200]))).astype(np.uint8)
+    lab_d, pr_d = torch.from_numpy(labels).to(dev), torch.from_numpy(preds).to(dev)
+    for kw in (dict(ignore_index=255), dict(), dict(ignore_index=255, other_bucket=True)):
+        cm, dropped = ssl.metrics.confusion_matrix(lab_d, pr_d, c, return_dropped=True, **kw)
+        o, od = oracle.confusion_matrix(labels.astype(np.int64), preds.astype(np.int64), c, **kw)
+        assert np.array_equal(cm.cpu().numpy(), o) and int(dropped) == od
+    # the same pixels as int64 through the generic kernel
+    cm64 = ssl.metrics.confusion_matrix(lab_d.long(), pr_d.long(), c, ignore_index=255)
+    assert torch.equal(cm64, ssl.metrics.confusion_matrix(lab_d, pr_d, c, ignore_index=255))
+
+
 @pytest.mark.parametrize("c,h,w", [(2, 256, 256), (19, 128, 260), (21, 65, 63)])
 def test_confusion_from_logits(ssl, dev, c, h, w):
     gen = torch.Generator().manual_seed(c + h)
