@@ -130,35 +130,64 @@ static int dice_blocks(int n, long long chw) {
 // is accumulated as integers; b200ssl_dice_from_cm turns it into metrics.py:1-7's value.
 // grid = (blocks, n); mask channel `fg` of mask [n, mask_channels, H, W].
 // ------------------------------------------------------------------------------------------
+// One warp per mask row (no per-pixel division), 4 consecutive pixels per lane (one 128-bit mask load when the
+// rows are 16-byte aligned); the argmax of a source pixel is reused by the neighbours that map to it.
 __global__ void __launch_bounds__(256)
 validation_cm_kernel(const float* __restrict__ logits, int C, int h, int w, const float* __restrict__ mask,
-                     int mask_channels, int H, int W, float thr, int fg, unsigned long long* __restrict__ cm) {
+                     int mask_channels, int H, int W, float thr, int fg, bool vec,
+                     unsigned long long* __restrict__ cm) {
   const int n = blockIdx.y;
   const float* __restrict__ lp = logits + (long long)n * C * h * w;
   const float* __restrict__ mp = mask + ((long long)n * mask_channels + fg) * (long long)H * W;
   const float sy = (float)h / (float)H, sx = (float)w / (float)W;
-  unsigned cnt[4] = {0u, 0u, 0u, 0u};
   const long long hw_low = (long long)h * w;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)H * W;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int y = (int)(i / W), x = (int)(i - (long long)y * W);
-    const int ys = min((int)floorf((float)y * sy), h - 1), xs = min((int)floorf((float)x * sx), w - 1);
-    const float* __restrict__ q = lp + (long long)ys * w + xs;
-    float best = __ldg(q);
-    int arg = 0;
-    for (int c = 1; c < C; ++c) {   // torch.argmax: first maximum wins, NaN counts as the maximum
-      const float v = __ldg(q + c * hw_low);
-      if (v > best || (v != v && best == best)) { best = v; arg = c; }
+  const int lane = (int)lane_id();
+  unsigned n_px = 0, n_m = 0, n_p = 0, n_mp = 0;          // pixels, mask fg, predicted fg, both
+  for (int y = blockIdx.x * 8 + (int)(threadIdx.x >> 5); y < H; y += (int)gridDim.x * 8) {
+    const int ys = min((int)floorf((float)y * sy), h - 1);
+    const float* __restrict__ lrow = lp + (long long)ys * w;
+    const float* __restrict__ mrow = mp + (long long)y * W;
+    for (int x0 = lane * 4; x0 < W; x0 += 128) {
+      float m[4] = {0.f, 0.f, 0.f, 0.f};
+      if (vec) {
+        const float4 v = ld_stream_f4(mrow + x0);
+        m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (x0 + e < W) m[e] = ld_stream_f1(mrow + x0 + e);
+      }
+      int last_xs = -1, p_fg = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (x0 + e < W) {
+          const int xs = min((int)floorf((float)(x0 + e) * sx), w - 1);
+          if (xs != last_xs) {
+            const float* __restrict__ q = lrow + xs;
+            float best = __ldg(q);
+            int arg = 0;
+            for (int c = 1; c < C; ++c) {   // torch.argmax: first maximum wins, NaN counts as the maximum
+              const float v = __ldg(q + c * hw_low);
+              if (v > best || (v != v && best == best)) { best = v; arg = c; }
+            }
+            p_fg = arg == fg ? 1 : 0;
+            last_xs = xs;
+          }
+          const unsigned m_fg = m[e] > thr ? 1u : 0u;
+          n_px += 1u;
+          n_m += m_fg;
+          n_p += (unsigned)p_fg;
+          n_mp += m_fg & (unsigned)p_fg;
+        }
+      }
     }
-    const int p_fg = arg == fg ? 1 : 0;
-    const int m_fg = ld_stream_f1(mp + i) > thr ? 1 : 0;
-    cnt[m_fg * 2 + p_fg] += 1u;
   }
+  const unsigned cnt[4] = {n_px - n_m - n_p + n_mp, n_p - n_mp, n_m - n_mp, n_mp};   // TN, FP, FN, TP
   __shared__ unsigned red[4][8];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const unsigned t = warp_sum(cnt[k]);
-    if (lane_id() == 0) red[k][threadIdx.x >> 5] = t;
+    if (lane == 0) red[k][threadIdx.x >> 5] = t;
   }
   __syncthreads();
   if (threadIdx.x < 4) {
@@ -238,13 +267,14 @@ int b200ssl_validation_cm(const float* logits, int n, int n_channels, int h, int
   B200SSL_REQUIRE(n <= 65535, "validation_cm: too many samples");
   if (n == 0 || H == 0 || W == 0) return 0;
   B200SSL_REQUIRE(logits && mask && cm_per_image, "validation_cm: null argument");
-  long long bx = ((long long)H * W + 256 * 8 - 1) / (256 * 8);
+  long long bx = (H + 7) / 8;                              // 8 rows (warps) per block and trip
   long long cap = (long long)kNumSMs * 8 / n;
   if (cap < 1) cap = 1;
   if (bx > cap) bx = cap;
+  const bool vec = aligned16(mask) && (W % 4 == 0);
   prof_begin("validation_cm", (cudaStream_t)stream);
   validation_cm_kernel<<<dim3((unsigned)bx, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(
-      logits, n_channels, h, w, mask, mask_channels, H, W, threshold, fg_class,
+      logits, n_channels, h, w, mask, mask_channels, H, W, threshold, fg_class, vec,
       reinterpret_cast<unsigned long long*>(cm_per_image));
   return check_launch("validation_cm");
 }
