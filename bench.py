@@ -715,7 +715,7 @@ def miou_sweep(b200ssl, args, rank, world, device):
                "value": round(pixels / (total_ms * 1e-3) / 1e6, 1), "unit": UNIT,
                "roofline": {"bound": "hbm", "alg_bytes_per_pixel": bpp, "achieved": round(gbps_gpu, 1), "peak": peak,
                             "unit": "GB/s", "frac": round(gbps_gpu / peak, 4), "peak_source": peak_src,
-                            "kernel": "confusion_kernel"},
+                            "kernel": "confusion_u8_kernel" if tag == "uint8" else "confusion_kernel"},
                "check": "exact" if int(flag) else "MISMATCH",
                "miou": round(float(b200ssl.metrics.miou_from_cm(cm_sum)), 6)}
         if world == 1:

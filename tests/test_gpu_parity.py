@@ -447,6 +447,8 @@ def test_confusion_uint8_run_stitching(ssl, dev, run, n_pixels):
         cm, dropped = ssl.metrics.confusion_matrix(lab_d, pr_d, c, return_dropped=True, **kw)
         o, od = oracle.confusion_matrix(labels.astype(np.int64), preds.astype(np.int64), c, **kw)
         assert np.array_equal(cm.cpu().numpy(), o) and int(dropped) == od
+        # without the dropped counter (the kernel's branch-light instantiation when there is no other bucket)
+        assert np.array_equal(ssl.metrics.confusion_matrix(lab_d, pr_d, c, **kw).cpu().numpy(), o)
     # the same pixels as int64 through the generic kernel
     cm64 = ssl.metrics.confusion_matrix(lab_d.long(), pr_d.long(), c, ignore_index=255)
     assert torch.equal(cm64, ssl.metrics.confusion_matrix(lab_d, pr_d, c, ignore_index=255))
