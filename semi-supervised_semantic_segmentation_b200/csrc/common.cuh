@@ -79,6 +79,10 @@ __device__ __forceinline__ float ld_stream_f1(const float* p) {
   return r;
 }
 
+// torch.argmax's ordering: x beats the running best iff x > best, or x is NaN while best is not (the first maximum
+// wins, NaN counts as the maximum).  Equivalent to !(x <= best) && best == best: two predicate instructions, no branch.
+__device__ __forceinline__ bool argmax_beats(float x, float best) { return !(x <= best) & (best == best); }
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;

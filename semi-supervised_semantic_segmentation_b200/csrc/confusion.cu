@@ -410,7 +410,7 @@ confusion_logits_kernel(const float* __restrict__ logits, const T* __restrict__ 
             const float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const bool take = (arg[e] < 0) || (x[e] > best[e]) || (x[e] != x[e] && best[e] == best[e]);
+              const bool take = (arg[e] < 0) || argmax_beats(x[e], best[e]);
               if (take) { best[e] = x[e]; arg[e] = c0 + u; }
             }
           }
@@ -421,7 +421,7 @@ confusion_logits_kernel(const float* __restrict__ logits, const T* __restrict__ 
         if (first + e < hw) {
           for (int c = 0; c < C; ++c) {
             const float x = logits[(long long)c * hw + first + e];
-            const bool take = (arg[e] < 0) || (x > best[e]) || (x != x && best[e] == best[e]);
+            const bool take = (arg[e] < 0) || argmax_beats(x, best[e]);
             if (take) { best[e] = x; arg[e] = c; }
           }
         }

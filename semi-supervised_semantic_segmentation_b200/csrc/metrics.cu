@@ -7,7 +7,7 @@ namespace b200ssl {
 
 // torch.argmax order: first maximal element wins, NaN counts as the maximum
 __device__ __forceinline__ void argmax_step(float x, int c, float& best, int& arg) {
-  const bool take = (arg < 0) || (x > best) || (x != x && best == best);
+  const bool take = (arg < 0) || argmax_beats(x, best);
   if (take) { best = x; arg = c; }
 }
 
@@ -168,7 +168,7 @@ validation_cm_kernel(const float* __restrict__ logits, int C, int h, int w, cons
             int arg = 0;
             for (int c = 1; c < C; ++c) {   // torch.argmax: first maximum wins, NaN counts as the maximum
               const float v = __ldg(q + c * hw_low);
-              if (v > best || (v != v && best == best)) { best = v; arg = c; }
+              if (argmax_beats(v, best)) { best = v; arg = c; }
             }
             p_fg = arg == fg ? 1 : 0;
             last_xs = xs;
