@@ -167,6 +167,16 @@ int b200ssl_mix2_field(const float* a0, const float* b0, float* out0, int c0, co
 #define B200SSL_LOVASZ_PRESENT 1
 #define B200SSL_LOVASZ_LIST 2
 #define B200SSL_LOVASZ_MAX_LIST 64
+/* error_mode: which per-pixel error is sorted.
+ *   ABS   : |fg - class_pred|, `probas` are probabilities                    (lovasz.py:193-200, lovasz_softmax_flat)
+ *   HINGE : 1 - logit * (2*label - 1), `probas` are raw logits [B,1,H,W]     (lovasz.py:96-111, lovasz_hinge_flat)
+ *           loss = dot(relu(errors_sorted), lovasz_grad(gt_sorted)).  Needs n_channels == 1 and class_mode LIST
+ *           with ONE entry, the foreground label (1); every other non-ignored label counts as background.
+ *           Pixels with error <= 0 carry relu = 0 and sit behind every positive error in the descending order, so
+ *           they are not sorted: gradient 0, and they are counted only in seg_fg / seg_valid.  The gradient is
+ *           with respect to the logits. */
+#define B200SSL_LOVASZ_ERR_ABS 0
+#define B200SSL_LOVASZ_ERR_HINGE 1
 
 typedef struct b200ssl_lovasz_desc {
   int32_t n_images;
@@ -179,7 +189,7 @@ typedef struct b200ssl_lovasz_desc {
   int32_t has_ignore;
   int64_t ignore_index;
   int32_t label_dtype;  /* b200ssl_label_dtype */
-  int32_t reserved_;
+  int32_t error_mode;   /* B200SSL_LOVASZ_ERR_* (0 for descriptors that predate the field) */
 } b200ssl_lovasz_desc;
 
 int32_t b200ssl_lovasz_num_segments(const b200ssl_lovasz_desc* d);

@@ -176,6 +176,46 @@ ORC_API double orc_lovasz_segment(const float* pred, const uint8_t* fg, long lon
   return loss;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * lovasz_hinge_flat, lovasz.py:96-111, on the L valid pixels of one image (or of the batch):
+ *   signs = 2*label - 1; errors = 1 - logits*signs (the product is exact, ONE rounding);
+ *   descending sort of the SIGNED errors (all of them, as the reference does; ties by ascending index);
+ *   loss = dot(relu(errors_sorted), lovasz_grad(gt_sorted)).
+ * grad[i] = dLoss/dlogit[i] = -sign_i * delta[rank(i)] where error_i > 0, else 0 (relu's backward).
+ * ------------------------------------------------------------------------------------------ */
+ORC_API double orc_lovasz_hinge_segment(const float* logits, const uint8_t* fg, long long L, float* grad) {
+  if (L <= 0) return 0.0;
+  orc_key* keys = (orc_key*)malloc((size_t)L * sizeof(orc_key));
+  long long G = 0;
+  for (long long i = 0; i < L; ++i) {
+    const float sx = fg[i] ? logits[i] : -logits[i];
+    keys[i].err = 1.0f - sx;
+    keys[i].idx = (int32_t)i;
+    G += fg[i] ? 1 : 0;
+  }
+  qsort(keys, (size_t)L, sizeof(orc_key), orc_key_cmp);
+  const float gts = (float)G;
+  long long cfg = 0, cbg = 0;
+  float jprev = 0.0f;
+  double loss = 0.0;
+  for (long long k = 0; k < L; ++k) {
+    const int32_t i = keys[k].idx;
+    if (fg[i]) ++cfg; else ++cbg;
+    const float j = 1.0f - (gts - (float)cfg) / (gts + (float)cbg);
+    const float d = (k == 0) ? j : (j - jprev);
+    jprev = j;
+    const float e = keys[k].err;
+    if (e > 0.0f) {
+      loss += (double)e * (double)d;
+      if (grad) grad[i] = fg[i] ? -d : d;
+    } else if (grad) {
+      grad[i] = 0.0f;
+    }
+  }
+  free(keys);
+  return loss;
+}
+
 /* lovasz.py:19-31 on an already sorted 0/1 vector (known-answer tests) */
 ORC_API void orc_lovasz_grad(const uint8_t* gt_sorted, long long p, float* out) {
   long long G = 0;

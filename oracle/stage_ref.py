@@ -22,8 +22,8 @@ REF_DIR = os.path.join(_HERE, "_ref")
 FILES = {
     "cowmix.py": "generate_gaussian :6-11, gaussian_kernel_2d_vertical :14-24, dual_pass_gaussian_fileter2d :27-37, "
                  "generate_cowmix_masks_like :40-69, mix_with_mask :72-73",
-    "lovasz.py": "lovasz_grad :19-31, iou :54-73, lovasz_softmax :155-170, lovasz_softmax_flat :173-201, "
-                 "flatten_probas :204-220, mean :235-253",
+    "lovasz.py": "lovasz_grad :19-31, iou :54-73, lovasz_hinge :79-111, flatten_binary_scores :114-126, "
+                 "lovasz_softmax :155-170, lovasz_softmax_flat :173-201, flatten_probas :204-220, mean :235-253",
     "losses.py": "CalculateLoss :8-22, binary_lovasz_loss_with_logits :239-250",
     "mean_teacher.py": "update_ema_variables :5-18, detach_model_parameters :20-22",
     "metrics.py": "dice_metric :1-7",

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libb200ssl.so")
 MAX_LIST = 64
 I64, I32, U8 = 0, 1, 2
 LOVASZ_ALL, LOVASZ_PRESENT, LOVASZ_LIST = 0, 1, 2
+LOVASZ_ERR_ABS, LOVASZ_ERR_HINGE = 0, 1
 EMA_CHUNK = 4096
 
 
@@ -27,7 +28,7 @@ class LovaszDesc(C.Structure):
         ("has_ignore", C.c_int32),
         ("ignore_index", C.c_int64),
         ("label_dtype", C.c_int32),
-        ("reserved_", C.c_int32),
+        ("error_mode", C.c_int32),
     ]
 
 

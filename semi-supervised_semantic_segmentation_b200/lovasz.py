@@ -4,6 +4,7 @@
     reference lovasz.py:173-201  lovasz_softmax_flat   (folded into the CUDA forward)
     reference lovasz.py:204-220  flatten_probas        (no copy here: NCHW is read in place)
     reference lovasz.py:19-31    lovasz_grad           (fused into the last radix pass)
+    reference lovasz.py:79-111   lovasz_hinge / lovasz_hinge_flat / flatten_binary_scores (same sort core, hinge errors)
     reference lovasz.py:54-73    iou / iou_binary      (derived from the confusion matrix)
 
 Forward computes the loss AND the unit gradient (sort rank -> Jaccard delta, scattered back to
@@ -157,6 +158,33 @@ def lovasz_softmax(probas, labels, classes='present', per_image=False, ignore=No
         return probas.permute(0, 2, 3, 1).reshape(-1, probas.shape[1]) * 0.  # lovasz.py:180-182
     desc = _make_desc(probas, labels, classes, per_image, ignore)
     loss, _, _ = _LovaszForward.apply(probas, labels, desc, True)
+    return loss
+
+
+# --------------------------- binary Lovasz hinge (lovasz.py:79-111) ------------------------------
+def lovasz_hinge(logits, labels, per_image=True, ignore=None):
+    """
+    Binary Lovasz hinge loss
+      logits: [B, H, W] logits at each pixel (between -infinity and +infinity)
+      labels: [B, H, W] Tensor, binary ground truth masks (0 or 1)
+      per_image: compute the loss per image instead of per batch
+      ignore: void class id
+    Same kernels as lovasz_softmax with the error 1 - logit * (2*label - 1) (one rounding, as the reference);
+    pixels whose error is <= 0 have relu(error) = 0 and sort behind every positive error, so they are never
+    sorted and get a zero gradient.  Labels other than 1 (and `ignore`) count as background.
+    """
+    require_cuda(logits, "logits", torch.float32)
+    require_cuda(labels, "labels")
+    if logits.dim() != 3 or tuple(labels.shape) != tuple(logits.shape):
+        raise ValueError(f"logits {tuple(logits.shape)} and labels {tuple(labels.shape)} must both be [B,H,W]")
+    if logits.numel() == 0:
+        if per_image and logits.shape[0] == 0:
+            return 0                      # mean of no images (lovasz.py:246)
+        return logits.sum() * 0.          # lovasz.py:103-105: only void pixels
+    x, labels = logits.unsqueeze(1).contiguous(), labels.contiguous()
+    desc = _make_desc(x, labels, [1], per_image, ignore)
+    desc.error_mode = _lib.LOVASZ_ERR_HINGE
+    loss, _, _ = _LovaszForward.apply(x, labels, desc, True)
     return loss
 
 

@@ -344,6 +344,36 @@ def sgd_case():
     save("sgd", **out)
 
 
+def hinge_case():
+    """lovasz.lovasz_hinge (lovasz.py:79-111) + autograd on seeded logits: per image / per batch, with and without a
+    void label, an image with only void pixels, an image without foreground, confident logits (most errors <= 0)."""
+    gen = torch.Generator().manual_seed(77)
+    out = {}
+    n, h, w = 3, 28, 36
+    lab = (coherent_labels(gen, n, 2, h, w, 7) > 0).long()
+    lab[2] = 0                                              # image 2: no foreground
+    lab_ign = lab.clone()
+    lab_ign[torch.rand(n, h, w, generator=gen) < 0.15] = 255
+    lab_ign[1] = 255                                        # image 1: only void pixels
+    noisy = torch.randn(n, h, w, generator=gen) * 2.0
+    confident = (2.0 * lab.float() - 1.0) * 3.0 + torch.randn(n, h, w, generator=gen) * 1.5   # mostly error <= 0
+    out["labels"], out["labels_ign"] = lab.numpy(), lab_ign.numpy()
+    out["logits_noisy"], out["logits_confident"] = noisy.numpy(), confident.numpy()
+    names = []
+    for lg_key, lg in (("logits_noisy", noisy), ("logits_confident", confident)):
+        for lab_key, lb, ignore in (("labels", lab, None), ("labels_ign", lab_ign, 255)):
+            for per_image in (True, False):
+                x = lg.clone().requires_grad_(True)
+                loss = ref_lovasz.lovasz_hinge(x, lb, per_image=per_image, ignore=ignore)
+                loss.backward()
+                name = f"{lg_key}|{lab_key}|{int(per_image)}|{ignore}"
+                out[name + "|loss"] = loss.detach().numpy()
+                out[name + "|grad"] = x.grad.numpy()
+                names.append(name)
+    out["cases"] = np.array(names)
+    save("lovasz_hinge", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:                       # regenerate selected files only: make_golden.py sgd_case ...
         for fn in sys.argv[1:]:
@@ -352,6 +382,7 @@ if __name__ == "__main__":
     cowmix_case("cowmix_small", 3, 40, 56, (0.4, 0.6), (1.0, 3.0), seed=3)
     cowmix_case("cowmix_c1", 2, 256, 256, (0.45, 0.55), (8, 32), seed=0)      # BASELINE configs[0]
     lovasz_cases()
+    hinge_case()
     binary_lovasz_case()
     ema_case()
     metrics_case()

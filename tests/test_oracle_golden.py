@@ -353,3 +353,16 @@ def test_validation_dice_oracle_vs_reference_golden():
         dice, cm = oracle.validation_dice(g[f"{tag}_pred"], g[f"{tag}_mask"])
         assert np.array_equal(dice.view(np.uint32), g[f"{tag}_dice"].view(np.uint32))
         assert int(cm.sum()) == g[f"{tag}_mask"].shape[0] * g[f"{tag}_mask"].shape[2] * g[f"{tag}_mask"].shape[3]
+
+
+def test_lovasz_hinge_oracle_vs_reference_golden():
+    """oracle.lovasz_hinge against lovasz.lovasz_hinge + autograd executed by the reference itself
+    (tests/golden/make_golden.py hinge_case; lovasz.py:79-111)."""
+    g = load_golden("lovasz_hinge")
+    for name in g["cases"]:
+        lg_key, lab_key, per_image, ignore = str(name).split("|")
+        ignore = None if ignore == "None" else int(ignore)
+        loss, grad = oracle.lovasz_hinge(g[lg_key], g[lab_key], per_image=bool(int(per_image)), ignore=ignore)
+        want = float(g[str(name) + "|loss"])
+        assert abs(float(loss) - want) <= 1e-5 * max(1.0, abs(want)), name
+        assert np.array_equal(grad, g[str(name) + "|grad"]), name   # deltas are integer-count arithmetic: exact
