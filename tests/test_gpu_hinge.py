@@ -137,3 +137,42 @@ def test_hinge_descriptor_is_checked(ssl, dev):
                                          meta.data_ptr(), meta.data_ptr() + 4, x.data_ptr(), ws.data_ptr(), ws.numel(),
                                          None)
     assert rc != 0 and b"error_mode" in _lib.lib.b200ssl_last_error()
+
+
+@pytest.mark.parametrize("per_image", [True, False])
+def test_hinge_fused_forward_backward(ssl, dev, per_image):
+    """b200ssl_lovasz_forward_backward with the hinge error: the last radix pass writes the FINAL gradient
+    RN(scale * delta) * sign for a known upstream gradient (here 0.5)."""
+    from b200ssl import _lib
+    rng = np.random.default_rng(21)
+    b, h, w = 3, 72, 100
+    labels = (rng.random((b, h, w)) < 0.4).astype(np.int64)
+    labels[rng.random((b, h, w)) < 0.05] = 255
+    logits = ((2.0 * (labels == 1) - 1.0) * 0.7 + rng.standard_normal((b, h, w)) * 1.5).astype(np.float32)
+    x = torch.from_numpy(logits).to(dev)
+    lab = torch.from_numpy(labels).to(dev)
+    d = _lib.LovaszDesc()
+    d.n_images, d.n_channels, d.hw, d.per_image = b, 1, h * w, int(per_image)
+    d.class_mode, d.n_list = _lib.LOVASZ_LIST, 1
+    d.class_list[0] = 1
+    d.has_ignore, d.ignore_index, d.label_dtype = 1, 255, _lib.I64
+    d.error_mode = _lib.LOVASZ_ERR_HINGE
+    n_seg = _lib.lib.b200ssl_lovasz_num_segments(C.byref(d))
+    assert n_seg == (b if per_image else 1)
+    ws = torch.empty(_lib.lib.b200ssl_lovasz_workspace_bytes(C.byref(d)), dtype=torch.uint8, device=dev)
+    go = torch.tensor([0.5], device=dev)
+    loss = torch.empty(1, device=dev)
+    seg_loss = torch.empty(n_seg, device=dev)
+    meta = torch.empty((2, n_seg), dtype=torch.int32, device=dev)
+    grad = torch.full_like(x, 7.0)
+    _lib.check(_lib.lib.b200ssl_lovasz_forward_backward(
+        C.byref(d), x.data_ptr(), lab.data_ptr(), go.data_ptr(), None, loss.data_ptr(), None, seg_loss.data_ptr(),
+        meta[0].data_ptr(), meta[1].data_ptr(), grad.data_ptr(), ws.data_ptr(), ws.numel(),
+        _lib.stream_ptr(dev)), "lovasz_forward_backward")
+    o_loss, o_grad = oracle.lovasz_hinge(logits, labels, per_image=per_image, ignore=255, grad_out=0.5)
+    assert abs(float(loss) - float(o_loss)) <= REL * max(1.0, abs(float(o_loss)))
+    assert np.array_equal(bits(grad.cpu().numpy() + 0.0), bits(o_grad + 0.0))
+    # seg_fg / seg_valid count every valid pixel, sorted or not
+    groups = [labels[i] for i in range(b)] if per_image else [labels]
+    assert meta[0].cpu().tolist() == [int((g == 1).sum()) for g in groups]
+    assert meta[1].cpu().tolist() == [int((g != 255).sum()) for g in groups]
