@@ -675,3 +675,21 @@ def test_loss_path_step_forked_equals_serial(ssl, dev):
         for k in ("mask", "mixed_images", "mixed_teacher", "grad", "cm", "labels"):
             assert torch.equal(o[k], outs[0][0][k]), k
         assert all(torch.equal(a, b) for a, b in zip(ema, outs[0][1]))
+
+
+@pytest.mark.parametrize("c", [100, 126, 127, 128])
+def test_confusion_uint8_many_classes(ssl, dev, c):
+    """uint8 labels with class counts whose matrix needs one shared-memory copy per block (c = 100), the opt-in
+    above 48 KB (c = 126, 127 with the other bucket = 128 x 128 bins = exactly the 64 KB budget) and the generic
+    kernel beyond it (c = 128 with the other bucket)."""
+    rng = np.random.default_rng(c)
+    n_pixels = 300_000
+    labels = np.repeat(rng.integers(0, c + 3, n_pixels // 10), rng.integers(1, 40, n_pixels // 10))[:n_pixels]
+    assert labels.size == n_pixels
+    labels = np.minimum(labels, 255).astype(np.uint8)
+    preds = np.where(rng.random(n_pixels) < 0.6, labels, rng.integers(0, c + 2, n_pixels)).astype(np.uint8)
+    lab_d, pr_d = torch.from_numpy(labels).to(dev), torch.from_numpy(preds).to(dev)
+    for kw in (dict(), dict(ignore_index=c + 1), dict(other_bucket=True), dict(ignore_index=3, other_bucket=True)):
+        cm = ssl.metrics.confusion_matrix(lab_d, pr_d, c, **kw)
+        o, _ = oracle.confusion_matrix(labels.astype(np.int64), preds.astype(np.int64), c, **kw)
+        assert np.array_equal(cm.cpu().numpy(), o), kw
