@@ -174,6 +174,8 @@ def lovasz_hinge(logits, labels, per_image=True, ignore=None):
     sorted and get a zero gradient.  Labels other than 1 (and `ignore`) count as background.
     """
     require_cuda(logits, "logits", torch.float32)
+    if torch.is_tensor(labels) and (labels.is_floating_point() or labels.dtype == torch.bool):
+        labels = labels.to(torch.int64)   # the reference takes float / bool masks too (`labels.float()`, lovasz.py:105)
     require_cuda(labels, "labels")
     if logits.dim() != 3 or tuple(labels.shape) != tuple(logits.shape):
         raise ValueError(f"logits {tuple(logits.shape)} and labels {tuple(labels.shape)} must both be [B,H,W]")

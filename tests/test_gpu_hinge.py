@@ -176,3 +176,15 @@ def test_hinge_fused_forward_backward(ssl, dev, per_image):
     groups = [labels[i] for i in range(b)] if per_image else [labels]
     assert meta[0].cpu().tolist() == [int((g == 1).sum()) for g in groups]
     assert meta[1].cpu().tolist() == [int((g != 255).sum()) for g in groups]
+
+
+def test_hinge_float_and_bool_masks(ssl, dev):
+    """the reference takes float (and bool) masks: `signs = 2. * labels.float() - 1.` (lovasz.py:105)"""
+    rng = np.random.default_rng(33)
+    labels = (rng.random((2, 30, 44)) < 0.5).astype(np.int64)
+    logits = rng.standard_normal((2, 30, 44)).astype(np.float32)
+    want, want_grad = oracle.lovasz_hinge(logits, labels, per_image=True)
+    for dtype in (torch.float32, torch.bool):
+        loss, grad = run(ssl, dev, logits, labels, dtype, per_image=True)
+        assert abs(loss - float(want)) <= REL * max(1.0, abs(float(want)))
+        assert np.array_equal(bits(grad + 0.0), bits(want_grad + 0.0))
