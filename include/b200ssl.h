@@ -315,6 +315,25 @@ int b200ssl_consistency_backward(const float* student, const float* teacher, int
                                  float threshold, const float* stats, const float* grad_out,
                                  float* grad_student, b200ssl_stream_t stream);
 
+/* The same loss with the teacher formed on the fly (SURVEY 8f N1 + N2): train.py:69-82 up-samples the two teacher
+ * predictions (F.interpolate bilinear, align_corners=False), mixes them with the CowMix mask
+ *     mixed_ema_pred = ema_pred_a * mask + ema_pred_b * (1 - mask)          (cowmix.py:72-73)
+ * and train.py:98-107 is that tensor's only consumer.  These entry points evaluate it in registers from
+ *     teacher_a / teacher_b  [n, c, th, tw]  (th x tw <= h x w; th == h and tw == w: read as they are),
+ *     mask [n, 1, h, w] ({0,1} fp32, the output of b200ssl_cowmix_mask / b200ssl_mix2_field),
+ * with the arithmetic of b200ssl_mix2_upsampled, so mixed_ema_pred is never written or read
+ * (4C + 4 + 8C/s^2 bytes per pixel instead of 12C + 4 + 8C/s^2 for mix + loss) and the results equal the
+ * two-step route: stats to the last bits of the fp64 partial sums, gradients bit for bit. */
+size_t b200ssl_consistency_mixed_workspace_bytes(int n, int h, int w);
+int b200ssl_consistency_mixed_forward(const float* student, const float* teacher_a, const float* teacher_b,
+                                      const float* mask, int n, int c, int h, int w, int th, int tw, float threshold,
+                                      float* stats_out, void* workspace, size_t workspace_bytes,
+                                      b200ssl_stream_t stream);
+int b200ssl_consistency_mixed_backward(const float* student, const float* teacher_a, const float* teacher_b,
+                                       const float* mask, int n, int c, int h, int w, int th, int tw, float threshold,
+                                       const float* stats, const float* grad_out, float* grad_student,
+                                       b200ssl_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Row N3: lovasz_softmax straight from logits.  lovasz.py:155-160 expects F.softmax(logits, 1); the
  * probabilities are never written here:

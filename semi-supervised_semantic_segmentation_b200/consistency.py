@@ -69,3 +69,67 @@ def confidence_masked_consistency(mixed_student_pred, mixed_ema_pred, confidence
     teacher = mixed_ema_pred.detach().contiguous()
     loss, stats = _Consistency.apply(student, teacher, confidence_threshold)
     return loss, stats[2]
+
+
+class _ConsistencyMixed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, student, teacher_a, teacher_b, mask, threshold):
+        dev = student.device
+        n, c, h, w = student.shape
+        th, tw = teacher_a.shape[2], teacher_a.shape[3]
+        stats = torch.empty(3, dtype=torch.float32, device=dev)
+        ws = _lib.workspaces.get(dev, "consistency", lib.b200ssl_consistency_mixed_workspace_bytes(n, h, w))
+        with torch.cuda.device(dev):
+            check(lib.b200ssl_consistency_mixed_forward(
+                student.data_ptr(), teacher_a.data_ptr(), teacher_b.data_ptr(), mask.data_ptr(), n, c, h, w, th, tw,
+                float(threshold), stats.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)), "consistency_mixed_forward")
+        ctx.save_for_backward(student, teacher_a, teacher_b, mask, stats)
+        ctx.threshold = float(threshold)
+        ctx.mark_non_differentiable(stats)
+        return stats[0], stats
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_stats):
+        student, teacher_a, teacher_b, mask, stats = ctx.saved_tensors
+        if g_loss is None or not ctx.needs_input_grad[0]:
+            return None, None, None, None, None
+        dev = student.device
+        n, c, h, w = student.shape
+        th, tw = teacher_a.shape[2], teacher_a.shape[3]
+        g = g_loss.to(torch.float32).contiguous()
+        grad = torch.empty_like(student)
+        with torch.cuda.device(dev):
+            check(lib.b200ssl_consistency_mixed_backward(
+                student.data_ptr(), teacher_a.data_ptr(), teacher_b.data_ptr(), mask.data_ptr(), n, c, h, w, th, tw,
+                ctx.threshold, stats.data_ptr(), g.data_ptr(), grad.data_ptr(), stream_ptr(dev)), "consistency_mixed_backward")
+        return grad, None, None, None, None
+
+
+def confidence_masked_consistency_mixed(mixed_student_pred, ema_pred_a, ema_pred_b, mask, confidence_threshold):
+    """train.py:69-82 + 98-107 with the teacher formed on the fly:
+
+        ema_pred_x      = F.interpolate(ema_pred_x, size, mode='bilinear', align_corners=False)   # if below `size`
+        mixed_ema_pred  = cowmix.mix_with_mask(ema_pred_a, ema_pred_b, mask)
+        loss, conf_mean = confidence_masked_consistency(mixed_student_pred, mixed_ema_pred, confidence_threshold)
+
+    `ema_pred_a` / `ema_pred_b`: the teacher's raw logits [N,C,h,w] at the network's resolution (h x w <= H x W of the
+    student prediction; equal sizes are read as they are), `mask` the CowMix mask [N,1,H,W].  The mixed teacher
+    prediction is never materialised; values and gradients equal the three-call route (gradients bit for bit)."""
+    require_cuda(mixed_student_pred, "mixed_student_pred", torch.float32)
+    require_cuda(ema_pred_a, "ema_pred_a", torch.float32)
+    require_cuda(ema_pred_b, "ema_pred_b", torch.float32)
+    require_cuda(mask, "mask", torch.float32)
+    s = mixed_student_pred
+    if s.dim() != 4 or ema_pred_a.dim() != 4 or ema_pred_a.shape != ema_pred_b.shape or \
+            ema_pred_a.shape[:2] != s.shape[:2]:
+        raise ValueError("student [N,C,H,W] and teacher predictions [N,C,h,w] (both teachers alike) expected")
+    if tuple(mask.shape) != (s.shape[0], 1, s.shape[2], s.shape[3]):
+        raise ValueError(f"mask must be [N,1,H,W] = {(s.shape[0], 1, s.shape[2], s.shape[3])}, got {tuple(mask.shape)}")
+    if s.numel() == 0 or ema_pred_a.numel() == 0:
+        raise ValueError("empty predictions")
+    if ema_pred_a.shape[2] > s.shape[2] or ema_pred_a.shape[3] > s.shape[3]:
+        raise ValueError("the teacher predictions must not be larger than the student's")
+    loss, stats = _ConsistencyMixed.apply(s.contiguous(), ema_pred_a.detach().contiguous(),
+                                          ema_pred_b.detach().contiguous(), mask.detach().contiguous(),
+                                          confidence_threshold)
+    return loss, stats[2]

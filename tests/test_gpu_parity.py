@@ -648,6 +648,69 @@ def test_consistency_no_confident_pixel_is_nan_like_the_reference(ssl, dev):
     assert torch.isnan(loss) and float(conf) == 0.0
 
 
+@pytest.mark.parametrize("n,c,H,W,th,tw,thr", [
+    (2, 2, 64, 96, 16, 24, 0.97),        # stride 4, vector path
+    (1, 19, 48, 64, 24, 32, 0.6),        # stride 2, 19 classes
+    (2, 3, 40, 56, 40, 56, 0.6),         # teacher at full resolution (read as it is)
+    (2, 2, 33, 47, 9, 12, 0.5),          # ragged ratio, W % 4 != 0 (scalar path)
+    (1, 2, 8, 8, 1, 1, 0.5),             # one teacher pixel
+    (4, 2, 256, 256, 64, 64, 0.97),
+])
+def test_consistency_mixed_equals_mix_then_loss(ssl, dev, n, c, H, W, th, tw, thr):
+    """train.py:69-82 + 98-107 with the teacher formed on the fly (b200ssl_consistency_mixed_*): the same values as
+    mix2_with_mask (low-resolution second pair) followed by confidence_masked_consistency -- confidence count
+    exact, gradients bit for bit, loss to the last bits of the fp64 partial sums -- and the oracle's
+    upsample -> mix -> loss chain within the float tolerance."""
+    gen = torch.Generator().manual_seed(n * 100 + c + H + th)
+    student = torch.randn(n, c, H, W, generator=gen) * 2
+    ta, tb = torch.randn(n, c, th, tw, generator=gen) * 3, torch.randn(n, c, th, tw, generator=gen) * 3
+    mask = (torch.nn.functional.avg_pool2d(torch.randn(n, 1, H, W, generator=gen), 5, 1, 2) > 0).float()
+    img = torch.zeros(n, 1, H, W)
+    d = lambda t: t.to(dev)
+    # three calls: (interpolate +) mix, then the loss
+    _, mixed = ssl.cowmix.mix2_with_mask(d(img), d(img), d(ta), d(tb), d(mask))
+    x1 = d(student).requires_grad_(True)
+    loss1, conf1 = ssl.consistency.confidence_masked_consistency(x1, mixed, thr)
+    (loss1 * 10.0).backward()
+    # fused
+    x2 = d(student).requires_grad_(True)
+    loss2, conf2 = ssl.consistency.confidence_masked_consistency_mixed(x2, d(ta), d(tb), d(mask), thr)
+    (loss2 * 10.0).backward()
+    assert float(conf1) == float(conf2)
+    if float(conf1) > 0:
+        assert abs(float(loss1) - float(loss2)) <= 1e-6 * abs(float(loss1))
+        assert torch.equal(x1.grad, x2.grad)
+    else:
+        assert torch.isnan(loss1) and torch.isnan(loss2)
+    # the oracle chain
+    up_a = oracle.upsample_bilinear(ta.numpy(), (H, W)) if (th, tw) != (H, W) else ta.numpy()
+    up_b = oracle.upsample_bilinear(tb.numpy(), (H, W)) if (th, tw) != (H, W) else tb.numpy()
+    o_mixed = oracle.mix(up_a, up_b, mask.numpy())
+    assert np.array_equal(o_mixed, mixed.cpu().numpy())
+    near = int((np.abs(1.0 / (1.0 + np.exp(-o_mixed.astype(np.float64))).max(1) - thr) < 1e-5).sum())
+    o_loss, o_conf, o_grad = oracle.consistency_loss(student.numpy(), o_mixed, thr, grad_out=10.0)
+    assert abs(float(conf2) - float(o_conf)) * n * H * W <= near + 1e-3
+    if near == 0 and float(o_conf) > 0:
+        assert abs(float(loss2) - float(o_loss)) <= REL * abs(float(o_loss))
+        got = x2.grad.cpu().numpy()
+        assert np.linalg.norm(got - o_grad) <= REL * np.linalg.norm(o_grad)
+
+
+def test_consistency_mixed_rejects_bad_shapes(ssl, dev):
+    s = torch.zeros(2, 2, 16, 16, device=dev)
+    t = torch.zeros(2, 2, 4, 4, device=dev)
+    m = torch.zeros(2, 1, 16, 16, device=dev)
+    f = ssl.consistency.confidence_masked_consistency_mixed
+    with pytest.raises(ValueError):
+        f(s, t, torch.zeros(2, 2, 4, 5, device=dev), m, 0.9)          # the two teachers differ
+    with pytest.raises(ValueError):
+        f(s, t, t, torch.zeros(2, 2, 16, 16, device=dev), 0.9)        # per-channel mask
+    with pytest.raises(ValueError):
+        f(s, torch.zeros(2, 2, 32, 32, device=dev), torch.zeros(2, 2, 32, 32, device=dev), m, 0.9)   # teacher larger
+    with pytest.raises(ValueError):
+        f(s, torch.zeros(2, 3, 4, 4, device=dev), torch.zeros(2, 3, 4, 4, device=dev), m, 0.9)       # channel mismatch
+
+
 def test_loss_path_step_forked_equals_serial(ssl, dev):
     """The internal fork/join of the three chains must not change a single bit, and work queued on the
     caller's stream right after the call must see all results."""
