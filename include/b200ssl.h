@@ -323,16 +323,18 @@ int b200ssl_consistency_backward(const float* student, const float* teacher, int
  *     mask [n, 1, h, w] ({0,1} fp32, the output of b200ssl_cowmix_mask / b200ssl_mix2_field),
  * with the arithmetic of b200ssl_mix2_upsampled, so mixed_ema_pred is never written or read
  * (4C + 4 + 8C/s^2 bytes per pixel instead of 12C + 4 + 8C/s^2 for mix + loss) and the results equal the
- * two-step route: stats to the last bits of the fp64 partial sums, gradients bit for bit. */
+ * two-step route: stats to the last bits of the fp64 partial sums, gradients bit for bit.
+ * conf_out / conf (optional, [n, h, w] bytes): the forward's per-pixel confidence decision; handing it to the
+ * backward saves it one evaluation of the teacher (without it the backward recomputes the decision). */
 size_t b200ssl_consistency_mixed_workspace_bytes(int n, int h, int w);
 int b200ssl_consistency_mixed_forward(const float* student, const float* teacher_a, const float* teacher_b,
                                       const float* mask, int n, int c, int h, int w, int th, int tw, float threshold,
-                                      float* stats_out, void* workspace, size_t workspace_bytes,
-                                      b200ssl_stream_t stream);
+                                      float* stats_out, unsigned char* conf_out, void* workspace,
+                                      size_t workspace_bytes, b200ssl_stream_t stream);
 int b200ssl_consistency_mixed_backward(const float* student, const float* teacher_a, const float* teacher_b,
                                        const float* mask, int n, int c, int h, int w, int th, int tw, float threshold,
-                                       const float* stats, const float* grad_out, float* grad_student,
-                                       b200ssl_stream_t stream);
+                                       const float* stats, const unsigned char* conf, const float* grad_out,
+                                       float* grad_student, b200ssl_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Row N3: lovasz_softmax straight from logits.  lovasz.py:155-160 expects F.softmax(logits, 1); the

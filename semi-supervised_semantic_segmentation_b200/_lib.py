@@ -105,8 +105,8 @@ SIGNATURES = {
     "b200ssl_consistency_forward": (_i, [_vp, _vp, _i, _i, _i64, C.c_float, _vp, _vp, _sz, _vp]),
     "b200ssl_consistency_backward": (_i, [_vp, _vp, _i, _i, _i64, C.c_float, _vp, _vp, _vp, _vp]),
     "b200ssl_consistency_mixed_workspace_bytes": (_sz, [_i, _i, _i]),
-    "b200ssl_consistency_mixed_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, C.c_float, _vp, _vp, _sz, _vp]),
-    "b200ssl_consistency_mixed_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, C.c_float, _vp, _vp, _vp, _vp]),
+    "b200ssl_consistency_mixed_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, C.c_float, _vp, _vp, _vp, _sz, _vp]),
+    "b200ssl_consistency_mixed_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, C.c_float, _vp, _vp, _vp, _vp, _vp]),
     "b200ssl_loss_path_step": (_i, [C.POINTER(StepDesc), _vp]),
     "b200ssl_loss_path_fork": (_i, [_vp]),
     "b200ssl_sizeof": (_sz, [_i]),

@@ -78,19 +78,21 @@ class _ConsistencyMixed(torch.autograd.Function):
         n, c, h, w = student.shape
         th, tw = teacher_a.shape[2], teacher_a.shape[3]
         stats = torch.empty(3, dtype=torch.float32, device=dev)
+        conf = torch.empty((n, h, w), dtype=torch.uint8, device=dev)     # the decision per pixel, for the backward
         ws = _lib.workspaces.get(dev, "consistency", lib.b200ssl_consistency_mixed_workspace_bytes(n, h, w))
         with torch.cuda.device(dev):
             check(lib.b200ssl_consistency_mixed_forward(
                 student.data_ptr(), teacher_a.data_ptr(), teacher_b.data_ptr(), mask.data_ptr(), n, c, h, w, th, tw,
-                float(threshold), stats.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)), "consistency_mixed_forward")
-        ctx.save_for_backward(student, teacher_a, teacher_b, mask, stats)
+                float(threshold), stats.data_ptr(), conf.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)),
+                "consistency_mixed_forward")
+        ctx.save_for_backward(student, teacher_a, teacher_b, mask, stats, conf)
         ctx.threshold = float(threshold)
         ctx.mark_non_differentiable(stats)
         return stats[0], stats
 
     @staticmethod
     def backward(ctx, g_loss, _g_stats):
-        student, teacher_a, teacher_b, mask, stats = ctx.saved_tensors
+        student, teacher_a, teacher_b, mask, stats, conf = ctx.saved_tensors
         if g_loss is None or not ctx.needs_input_grad[0]:
             return None, None, None, None, None
         dev = student.device
@@ -101,11 +103,12 @@ class _ConsistencyMixed(torch.autograd.Function):
         with torch.cuda.device(dev):
             check(lib.b200ssl_consistency_mixed_backward(
                 student.data_ptr(), teacher_a.data_ptr(), teacher_b.data_ptr(), mask.data_ptr(), n, c, h, w, th, tw,
-                ctx.threshold, stats.data_ptr(), g.data_ptr(), grad.data_ptr(), stream_ptr(dev)), "consistency_mixed_backward")
+                ctx.threshold, stats.data_ptr(), conf.data_ptr(), g.data_ptr(), grad.data_ptr(), stream_ptr(dev)),
+                "consistency_mixed_backward")
         return grad, None, None, None, None
 
 
-def confidence_masked_consistency_mixed(mixed_student_pred, ema_pred_a, ema_pred_b, mask, confidence_threshold):
+def confidence_masked_consistency_mixed(mixed_student_pred, ema_pred_a, ema_pred_b, mask, confidence_threshold, fused=None):
     """train.py:69-82 + 98-107 with the teacher formed on the fly:
 
         ema_pred_x      = F.interpolate(ema_pred_x, size, mode='bilinear', align_corners=False)   # if below `size`
@@ -114,7 +117,12 @@ def confidence_masked_consistency_mixed(mixed_student_pred, ema_pred_a, ema_pred
 
     `ema_pred_a` / `ema_pred_b`: the teacher's raw logits [N,C,h,w] at the network's resolution (h x w <= H x W of the
     student prediction; equal sizes are read as they are), `mask` the CowMix mask [N,1,H,W].  The mixed teacher
-    prediction is never materialised; values and gradients equal the three-call route (gradients bit for bit)."""
+    prediction is never materialised; values and gradients equal the three-call route (gradients bit for bit).
+    fused=None chooses by the channel count: forming the teacher in registers costs one more interpolation of both
+    teacher tensors in the backward pass, which pays for few channels (1.22x over mix + loss at C = 2, the reference's
+    configuration) and does not at 19 (0.84x: the interpolation is instruction-bound, benchmarks/consistency_mixed.py);
+    above 4 channels the wrapper therefore materialises the mixed teacher with ONE mix2_upsampled launch and calls the
+    two-tensor loss.  fused=True / False force either route (same results)."""
     require_cuda(mixed_student_pred, "mixed_student_pred", torch.float32)
     require_cuda(ema_pred_a, "ema_pred_a", torch.float32)
     require_cuda(ema_pred_b, "ema_pred_b", torch.float32)
@@ -129,6 +137,13 @@ def confidence_masked_consistency_mixed(mixed_student_pred, ema_pred_a, ema_pred
         raise ValueError("empty predictions")
     if ema_pred_a.shape[2] > s.shape[2] or ema_pred_a.shape[3] > s.shape[3]:
         raise ValueError("the teacher predictions must not be larger than the student's")
+    if fused is None:
+        fused = s.shape[1] <= 4
+    if not fused:
+        from . import cowmix
+        dummy = mask.detach()                      # first pair of the fused mix: one channel, discarded
+        _, mixed = cowmix.mix2_with_mask(dummy, dummy, ema_pred_a.detach(), ema_pred_b.detach(), mask.detach())
+        return confidence_masked_consistency(s, mixed, confidence_threshold)
     loss, stats = _ConsistencyMixed.apply(s.contiguous(), ema_pred_a.detach().contiguous(),
                                           ema_pred_b.detach().contiguous(), mask.detach().contiguous(),
                                           confidence_threshold)

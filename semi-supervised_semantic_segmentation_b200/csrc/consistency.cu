@@ -204,10 +204,11 @@ __device__ __forceinline__ void load_row_vec(const float* __restrict__ p, float 
 }
 
 template <int VEC, bool LOWRES>
-__global__ void __launch_bounds__(kConsThreads)
+__global__ void __launch_bounds__(kConsThreads, 3)
 consistency_mixed_partial_kernel(const float* __restrict__ student, const float* __restrict__ ta,
                                  const float* __restrict__ tb, const float* __restrict__ mask, int C, int h, int w,
-                                 int th, int tw, float thr, double* __restrict__ partials) {
+                                 int th, int tw, float thr, double* __restrict__ partials,
+                                 unsigned char* __restrict__ conf_out) {
   const int n = blockIdx.y;
   const long long hw = (long long)h * w, t_plane = (long long)th * tw;
   const float* __restrict__ sp = student + (long long)n * C * hw;
@@ -248,12 +249,18 @@ consistency_mixed_partial_kernel(const float* __restrict__ student, const float*
         tmax[e] = fmaxf(tmax[e], t);
       }
     }
+    unsigned char cf[VEC];
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      if (tmax[e] > thr) {
+      cf[e] = tmax[e] > thr ? 1 : 0;
+      if (cf[e]) {
         s_conf += 1.0;
         s_loss += (double)sq[e];
       }
+    }
+    if (conf_out) {   // the confidence decision, kept for the backward pass (one byte per pixel)
+      if (VEC == 4) *reinterpret_cast<uchar4*>(conf_out + (long long)n * hw + off) = make_uchar4(cf[0], cf[VEC > 1 ? 1 : 0], cf[VEC > 2 ? 2 : 0], cf[VEC > 3 ? 3 : 0]);
+      else conf_out[(long long)n * hw + off] = cf[0];
     }
   }
   __shared__ double red[2][kConsThreads / 32];
@@ -271,11 +278,12 @@ consistency_mixed_partial_kernel(const float* __restrict__ student, const float*
 }
 
 template <int VEC, bool LOWRES>
-__global__ void __launch_bounds__(kConsThreads)
+__global__ void __launch_bounds__(kConsThreads, 3)
 consistency_mixed_grad_kernel(const float* __restrict__ student, const float* __restrict__ ta,
                               const float* __restrict__ tb, const float* __restrict__ mask, int C, int h, int w,
                               int th, int tw, float thr, const float* __restrict__ stats,
-                              const float* __restrict__ grad_out, float* __restrict__ grad) {
+                              const float* __restrict__ grad_out, float* __restrict__ grad,
+                              const unsigned char* __restrict__ conf_in) {
   const int n = blockIdx.y;
   const long long hw = (long long)h * w, t_plane = (long long)th * tw;
   const float* __restrict__ sp = student + (long long)n * C * hw;
@@ -302,19 +310,30 @@ consistency_mixed_grad_kernel(const float* __restrict__ student, const float* __
 #pragma unroll
       for (int e = 0; e < VEC; ++e) taps.tx[e] = axis_tap(x + e, tw, sx);
     }
-    // pass 1: confidence from the largest mixed teacher logit (sigmoid is monotone), pass 2: the gradient
-    float tmax[VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) tmax[e] = -INFINITY;
-    for (int c = 0; c < C; ++c) {
-      float tv[VEC];
-      mixed_teacher<VEC, LOWRES>(ap, bp, c, t_plane, tw, off, taps, m, om, tv);
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) tmax[e] = fmaxf(tmax[e], tv[e]);
-    }
+    // the confidence decision: the forward pass's byte per pixel, or (pass 1) from the largest mixed teacher logit
+    // (sigmoid is monotone); then (pass 2) the gradient
     float conf[VEC];
+    if (conf_in) {
+      if (VEC == 4) {
+        const uchar4 cb = __ldg(reinterpret_cast<const uchar4*>(conf_in + (long long)n * hw + off));
+        conf[0] = cb.x ? 1.0f : 0.0f; conf[VEC > 1 ? 1 : 0] = cb.y ? 1.0f : 0.0f;
+        conf[VEC > 2 ? 2 : 0] = cb.z ? 1.0f : 0.0f; conf[VEC > 3 ? 3 : 0] = cb.w ? 1.0f : 0.0f;
+      } else {
+        conf[0] = conf_in[(long long)n * hw + off] ? 1.0f : 0.0f;
+      }
+    } else {
+      float tmax[VEC];
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) conf[e] = sigmoidf_rn(tmax[e]) > thr ? 1.0f : 0.0f;
+      for (int e = 0; e < VEC; ++e) tmax[e] = -INFINITY;
+      for (int c = 0; c < C; ++c) {
+        float tv[VEC];
+        mixed_teacher<VEC, LOWRES>(ap, bp, c, t_plane, tw, off, taps, m, om, tv);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) tmax[e] = fmaxf(tmax[e], tv[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) conf[e] = sigmoidf_rn(tmax[e]) > thr ? 1.0f : 0.0f;
+    }
     for (int c = 0; c < C; ++c) {
       float sv[VEC], tv[VEC], g[VEC];
       load_row_vec<VEC>(sp + (long long)c * hw + off, sv);
@@ -418,11 +437,12 @@ int mixed_args(const char* who, const float* student, const float* ta, const flo
 
 int b200ssl_consistency_mixed_forward(const float* student, const float* teacher_a, const float* teacher_b,
                                       const float* mask, int n, int c, int h, int w, int th, int tw, float threshold,
-                                      float* stats_out, void* workspace, size_t workspace_bytes,
-                                      b200ssl_stream_t stream) {
+                                      float* stats_out, unsigned char* conf_out, void* workspace,
+                                      size_t workspace_bytes, b200ssl_stream_t stream) {
   using namespace b200ssl;
   MixedArgs a;
   int rc = mixed_args("consistency_mixed_forward", student, teacher_a, teacher_b, mask, n, c, h, w, th, tw, nullptr, &a);
+  if (conf_out && (reinterpret_cast<uintptr_t>(conf_out) & 3u)) a.vec = false;
   if (rc) return rc;
   B200SSL_REQUIRE(stats_out, "consistency_mixed_forward: null argument");
   const size_t need = (size_t)n * a.bx * 2 * sizeof(double);
@@ -435,7 +455,7 @@ int b200ssl_consistency_mixed_forward(const float* student, const float* teacher
   double* part = static_cast<double*>(workspace);
   prof_begin("consistency_mixed_partial", s);
 #define LAUNCH(V, L) \
-  consistency_mixed_partial_kernel<V, L><<<grid, kConsThreads, 0, s>>>(student, teacher_a, teacher_b, mask, c, h, w, th, tw, threshold, part)
+  consistency_mixed_partial_kernel<V, L><<<grid, kConsThreads, 0, s>>>(student, teacher_a, teacher_b, mask, c, h, w, th, tw, threshold, part, conf_out)
   if (a.vec) { if (a.lowres) LAUNCH(4, true); else LAUNCH(4, false); }
   else       { if (a.lowres) LAUNCH(1, true); else LAUNCH(1, false); }
 #undef LAUNCH
@@ -448,18 +468,19 @@ int b200ssl_consistency_mixed_forward(const float* student, const float* teacher
 
 int b200ssl_consistency_mixed_backward(const float* student, const float* teacher_a, const float* teacher_b,
                                        const float* mask, int n, int c, int h, int w, int th, int tw, float threshold,
-                                       const float* stats, const float* grad_out, float* grad_student,
-                                       b200ssl_stream_t stream) {
+                                       const float* stats, const unsigned char* conf, const float* grad_out,
+                                       float* grad_student, b200ssl_stream_t stream) {
   using namespace b200ssl;
   MixedArgs a;
   int rc = mixed_args("consistency_mixed_backward", student, teacher_a, teacher_b, mask, n, c, h, w, th, tw, grad_student, &a);
+  if (conf && (reinterpret_cast<uintptr_t>(conf) & 3u)) a.vec = false;
   if (rc) return rc;
   B200SSL_REQUIRE(stats && grad_out && grad_student, "consistency_mixed_backward: null argument");
   cudaStream_t s = (cudaStream_t)stream;
   const dim3 grid((unsigned)a.bx, (unsigned)n);
   prof_begin("consistency_mixed_grad", s);
 #define LAUNCH(V, L) \
-  consistency_mixed_grad_kernel<V, L><<<grid, kConsThreads, 0, s>>>(student, teacher_a, teacher_b, mask, c, h, w, th, tw, threshold, stats, grad_out, grad_student)
+  consistency_mixed_grad_kernel<V, L><<<grid, kConsThreads, 0, s>>>(student, teacher_a, teacher_b, mask, c, h, w, th, tw, threshold, stats, grad_out, grad_student, conf)
   if (a.vec) { if (a.lowres) LAUNCH(4, true); else LAUNCH(4, false); }
   else       { if (a.lowres) LAUNCH(1, true); else LAUNCH(1, false); }
 #undef LAUNCH

@@ -674,14 +674,35 @@ def test_consistency_mixed_equals_mix_then_loss(ssl, dev, n, c, H, W, th, tw, th
     (loss1 * 10.0).backward()
     # fused
     x2 = d(student).requires_grad_(True)
-    loss2, conf2 = ssl.consistency.confidence_masked_consistency_mixed(x2, d(ta), d(tb), d(mask), thr)
+    loss2, conf2 = ssl.consistency.confidence_masked_consistency_mixed(x2, d(ta), d(tb), d(mask), thr, fused=True)
     (loss2 * 10.0).backward()
+    # the wrapper's own choice of route (by channel count) gives the same numbers
+    x4 = d(student).requires_grad_(True)
+    loss4, conf4 = ssl.consistency.confidence_masked_consistency_mixed(x4, d(ta), d(tb), d(mask), thr)
+    (loss4 * 10.0).backward()
+    assert float(conf4) == float(conf2) and (float(conf2) == 0 or torch.equal(x4.grad, x2.grad))
     assert float(conf1) == float(conf2)
     if float(conf1) > 0:
         assert abs(float(loss1) - float(loss2)) <= 1e-6 * abs(float(loss1))
         assert torch.equal(x1.grad, x2.grad)
     else:
         assert torch.isnan(loss1) and torch.isnan(loss2)
+    # straight through the C ABI without the confidence bytes: the backward recomputes the decision
+    from b200ssl import _lib
+    import ctypes as C
+    xs, a_d, b_d, m_d = d(student), d(ta), d(tb), d(mask)
+    stats = torch.empty(3, device=dev)
+    ws = torch.empty(max(int(_lib.lib.b200ssl_consistency_mixed_workspace_bytes(n, H, W)), 16), dtype=torch.uint8, device=dev)
+    go = torch.tensor([10.0], device=dev)
+    g3 = torch.empty_like(xs)
+    _lib.check(_lib.lib.b200ssl_consistency_mixed_forward(xs.data_ptr(), a_d.data_ptr(), b_d.data_ptr(), m_d.data_ptr(),
+                                                          n, c, H, W, th, tw, thr, stats.data_ptr(), None, ws.data_ptr(),
+                                                          ws.numel(), _lib.stream_ptr(dev)), "consistency_mixed_forward")
+    _lib.check(_lib.lib.b200ssl_consistency_mixed_backward(xs.data_ptr(), a_d.data_ptr(), b_d.data_ptr(), m_d.data_ptr(),
+                                                           n, c, H, W, th, tw, thr, stats.data_ptr(), None, go.data_ptr(),
+                                                           g3.data_ptr(), _lib.stream_ptr(dev)), "consistency_mixed_backward")
+    if float(conf1) > 0:
+        assert torch.equal(g3, x2.grad) and float(stats[2]) == float(conf2)
     # the oracle chain
     up_a = oracle.upsample_bilinear(ta.numpy(), (H, W)) if (th, tw) != (H, W) else ta.numpy()
     up_b = oracle.upsample_bilinear(tb.numpy(), (H, W)) if (th, tw) != (H, W) else tb.numpy()
